@@ -1,0 +1,188 @@
+// Short-Weierstrass (a = 0) point arithmetic for the bucket method, generic over the coordinate field
+// (Fp for G1 / Pasta, Fp2 for G2).
+//
+// Replaces on the reference's hot path:
+//   mixedSum_vartime / sum_vartime / double   reference constantine/math/elliptic/ec_shortweierstrass_jacobian.nim:798-896, 681-796, 564-610
+// The reference accumulates buckets in Jacobian (8M+3S mixed add) or batched-affine form; on the GPU every
+// bucket lives in extended-Jacobian "XYZZ" coordinates (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2): the mixed add is
+// 8M+2S and never needs a Z that is not already squared/cubed. The reference ships the same system
+// (ec_shortweierstrass_jacobian_extended.nim:30-40, 258-310) but does not use it in its MSM. Any coordinate
+// system yields the same group element, which is what parity is defined on (affine-normalised equality,
+// reference tests/parallel/t_ec_template_parallel.nim:188).
+//
+// All special cases are exact: infinity operands (affine infinity is (0,0), reference
+// ec_shortweierstrass_affine.nim:52-62; XYZZ infinity is ZZ == 0), P + P (doubling), P + (-P).
+#pragma once
+#include "field.cuh"
+
+namespace b200 {
+
+template <class T>
+struct Aff {
+  T x, y;
+  B200_DEV bool is_inf() const { return x.is_zero() && y.is_zero(); }
+};
+
+template <class T>
+struct Xyzz {
+  T x, y, zz, zzz;
+  B200_DEV static Xyzz inf() { Xyzz r; r.x = T::zero(); r.y = T::zero(); r.zz = T::zero(); r.zzz = T::zero(); return r; }
+  B200_DEV bool is_inf() const { return zz.is_zero(); }
+  B200_DEV static Xyzz from_affine(const Aff<T>& p) {
+    Xyzz r;
+    if (p.is_inf()) return inf();
+    r.x = p.x; r.y = p.y; r.zz = T::one(); r.zzz = T::one();
+    return r;
+  }
+};
+
+// ---- global-memory (de)serialisation: an ABI struct is a flat array of 32-bit words (little-endian limbs) ----
+template <class T>
+B200_DEV void load_words(T& v, const uint32_t* __restrict__ p) {
+  static_assert(T::WORDS % 4 == 0, "16-byte multiple");
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int k = 0; k < T::WORDS / 4; k++) {
+    uint4 w = __ldg(q + k);
+    v.set_word(4 * k + 0, w.x); v.set_word(4 * k + 1, w.y); v.set_word(4 * k + 2, w.z); v.set_word(4 * k + 3, w.w);
+  }
+}
+template <class T>
+B200_DEV void load_words_rw(T& v, const uint32_t* p) {  // plain (coherent) loads for buffers written by earlier kernels
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int k = 0; k < T::WORDS / 4; k++) {
+    uint4 w = q[k];
+    v.set_word(4 * k + 0, w.x); v.set_word(4 * k + 1, w.y); v.set_word(4 * k + 2, w.z); v.set_word(4 * k + 3, w.w);
+  }
+}
+template <class T>
+B200_DEV void store_words(uint32_t* p, const T& v) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int k = 0; k < T::WORDS / 4; k++) {
+    uint4 w;
+    w.x = v.word(4 * k + 0); w.y = v.word(4 * k + 1); w.z = v.word(4 * k + 2); w.w = v.word(4 * k + 3);
+    q[k] = w;
+  }
+}
+
+template <class T>
+B200_DEV Aff<T> load_affine(const uint32_t* __restrict__ base, uint32_t idx) {
+  const uint32_t* p = base + (size_t)idx * (2 * T::WORDS);
+  Aff<T> a;
+  load_words(a.x, p);
+  load_words(a.y, p + T::WORDS);
+  return a;
+}
+template <class T>
+B200_DEV Xyzz<T> load_xyzz(const uint32_t* base, size_t idx) {
+  const uint32_t* p = base + idx * (4 * T::WORDS);
+  Xyzz<T> a;
+  load_words_rw(a.x, p);
+  load_words_rw(a.y, p + T::WORDS);
+  load_words_rw(a.zz, p + 2 * T::WORDS);
+  load_words_rw(a.zzz, p + 3 * T::WORDS);
+  return a;
+}
+template <class T>
+B200_DEV void store_xyzz(uint32_t* base, size_t idx, const Xyzz<T>& a) {
+  uint32_t* p = base + idx * (4 * T::WORDS);
+  store_words(p, a.x);
+  store_words(p + T::WORDS, a.y);
+  store_words(p + 2 * T::WORDS, a.zz);
+  store_words(p + 3 * T::WORDS, a.zzz);
+}
+
+// ---- group law ------------------------------------------------------------------------------------------
+
+// 2*(x,y) for an affine, finite point: mdbl-2008-s-1 with a = 0.  (y == 0 gives ZZ = 0 = infinity, correct.)
+template <class T>
+B200_DEV Xyzz<T> xyzz_dbl_affine(const Aff<T>& p) {
+  T U = p.y.dbl();
+  T V = U.sqr();
+  T W = U * V;
+  T S = p.x * V;
+  T X2 = p.x.sqr();
+  T M = X2.dbl() + X2;
+  Xyzz<T> r;
+  r.x = M.sqr() - S.dbl();
+  r.y = M * (S - r.x) - W * p.y;
+  r.zz = V;
+  r.zzz = W;
+  return r;
+}
+
+// 2*P, dbl-2008-s-1 with a = 0
+template <class T>
+B200_DEV Xyzz<T> xyzz_dbl(const Xyzz<T>& p) {
+  T U = p.y.dbl();
+  T V = U.sqr();
+  T W = U * V;
+  T S = p.x * V;
+  T X2 = p.x.sqr();
+  T M = X2.dbl() + X2;
+  Xyzz<T> r;
+  r.x = M.sqr() - S.dbl();
+  r.y = M * (S - r.x) - W * p.y;
+  r.zz = V * p.zz;     // infinity (ZZ = 0) stays infinity
+  r.zzz = W * p.zzz;
+  return r;
+}
+
+// acc += q  (q affine, finite or infinity): madd-2008-s, 8M + 2S on the generic path.
+template <class T>
+B200_DEV void xyzz_madd(Xyzz<T>& acc, const Aff<T>& q) {
+  if (q.is_inf()) return;
+  if (acc.is_inf()) {
+    acc.x = q.x; acc.y = q.y; acc.zz = T::one(); acc.zzz = T::one();
+    return;
+  }
+  T U2 = q.x * acc.zz;
+  T S2 = q.y * acc.zzz;
+  T P = U2 - acc.x;
+  T R = S2 - acc.y;
+  if (P.is_zero()) {
+    if (R.is_zero()) acc = xyzz_dbl_affine(q);
+    else acc = Xyzz<T>::inf();
+    return;
+  }
+  T PP = P.sqr();
+  T PPP = P * PP;
+  T Q = acc.x * PP;
+  T X3 = R.sqr() - PPP - Q.dbl();
+  T Y3 = R * (Q - X3) - acc.y * PPP;
+  acc.x = X3;
+  acc.y = Y3;
+  acc.zz = acc.zz * PP;
+  acc.zzz = acc.zzz * PPP;
+}
+
+// acc += q  (both XYZZ): add-2008-s, 12M + 2S on the generic path.
+template <class T>
+B200_DEV void xyzz_add(Xyzz<T>& acc, const Xyzz<T>& q) {
+  if (q.is_inf()) return;
+  if (acc.is_inf()) { acc = q; return; }
+  T U1 = acc.x * q.zz;
+  T U2 = q.x * acc.zz;
+  T S1 = acc.y * q.zzz;
+  T S2 = q.y * acc.zzz;
+  T P = U2 - U1;
+  T R = S2 - S1;
+  if (P.is_zero()) {
+    if (R.is_zero()) acc = xyzz_dbl(acc);
+    else acc = Xyzz<T>::inf();
+    return;
+  }
+  T PP = P.sqr();
+  T PPP = P * PP;
+  T Q = U1 * PP;
+  T X3 = R.sqr() - PPP - Q.dbl();
+  T Y3 = R * (Q - X3) - S1 * PPP;
+  acc.x = X3;
+  acc.y = Y3;
+  acc.zz = acc.zz * q.zz * PP;
+  acc.zzz = acc.zzz * q.zzz * PPP;
+}
+
+}  // namespace b200

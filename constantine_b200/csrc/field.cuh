@@ -1,0 +1,289 @@
+// Prime-field and quadratic-extension arithmetic for sm_100a, register-resident, 32-bit limbs.
+//
+// What this replaces on the reference's hot path:
+//   Fp.prod / square -> mulMont -> mulMont_CIOS_sparebit   reference constantine/math/arithmetic/limbs_montgomery.nim:180-217, 484-522
+//   Fp.sum / diff / double / neg                            reference constantine/math/arithmetic/finite_fields.nim:172-266
+//   Fp2 complex mul / sqr (i^2 = -1)                        reference constantine/math/extension_fields/towers.nim:798-885
+//
+// Same values as the reference (Montgomery residues a*R mod p with R = 2^(64*limbs64), canonical i.e. always
+// fully reduced to [0, p)), different machine mapping: the B200 integer datapath is 32 bits wide
+// (IMAD / IMAD.WIDE.U32 on the FMA pipe), so a 64-bit-limb value is processed as 2x as many 32-bit limbs --
+// the little-endian byte image is identical, so ABI structs are loaded/stored as-is.
+//
+// Montgomery multiplication: operand-scanning CIOS where the 32x32->64 partial products are kept in two
+// accumulator rows, one holding products that start on even limb positions and one holding products that
+// start on odd positions. Inside a row every (lo,hi) product pair lands on an aligned limb pair, so a whole
+// row update is ONE carry chain of mad.lo.cc / madc.hi.cc (ptxas pairs them into IMAD.WIDE.U32[.X]).
+// Dividing by 2^32 at the end of each outer iteration swaps the roles of the two rows.
+#pragma once
+#include <cstdint>
+#include "field_constants.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX carry-chain primitives. `volatile` keeps program order, which is what keeps the CC flag meaningful
+// between consecutive statements (NVVM never emits .cc instructions on its own).
+// ---------------------------------------------------------------------------------------------------------
+#define B200_DEV __device__ __forceinline__
+
+B200_DEV uint32_t p_add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B200_DEV uint32_t p_addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B200_DEV uint32_t p_addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B200_DEV uint32_t p_sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B200_DEV uint32_t p_subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B200_DEV uint32_t p_subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B200_DEV uint32_t p_mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B200_DEV uint32_t p_mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B200_DEV uint32_t p_mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+B200_DEV uint32_t p_madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+B200_DEV uint32_t p_madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+B200_DEV uint32_t p_madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+
+// ---------------------------------------------------------------------------------------------------------
+// Raw limb-array kernels, F = one of the generated field-constant structs (F::N even).
+// ---------------------------------------------------------------------------------------------------------
+
+// r = a + b, returns carry-out
+template <int N>
+B200_DEV uint32_t limbs_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  r[0] = p_add_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < N; i++) r[i] = p_addc_cc(a[i], b[i]);
+  return p_addc(0, 0);
+}
+
+// r = a - b, returns borrow mask (0xFFFFFFFF if a < b else 0)
+template <int N>
+B200_DEV uint32_t limbs_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  r[0] = p_sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < N; i++) r[i] = p_subc_cc(a[i], b[i]);
+  return p_subc(0, 0);
+}
+
+// if (r >= p) r -= p      (r < 2p on entry)
+template <class F>
+B200_DEV void final_sub(uint32_t* r) {
+  constexpr int N = F::N;
+  uint32_t t[N];
+  t[0] = p_sub_cc(r[0], F::P(0));
+#pragma unroll
+  for (int i = 1; i < N; i++) t[i] = p_subc_cc(r[i], F::P(i));
+  uint32_t borrow = p_subc(0, 0);  // all-ones if r < p
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = borrow ? r[i] : t[i];
+}
+
+template <class F>
+B200_DEV void fe_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  // a, b < p < 2^(32N - 1): the sum cannot carry out of N limbs (every field here has >= 1 spare bit).
+  limbs_add<F::N>(r, a, b);
+  final_sub<F>(r);
+}
+
+template <class F>
+B200_DEV void fe_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  constexpr int N = F::N;
+  uint32_t borrow = limbs_sub<N>(r, a, b);
+  // add back p under the borrow mask
+  r[0] = p_add_cc(r[0], F::P(0) & borrow);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) r[i] = p_addc_cc(r[i], F::P(i) & borrow);
+  r[N - 1] = p_addc(r[N - 1], F::P(N - 1) & borrow);
+}
+
+template <class F>
+B200_DEV void fe_neg(uint32_t* r, const uint32_t* a) {
+  constexpr int N = F::N;
+  uint32_t nz = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) nz |= a[i];
+  uint32_t t[N];
+  t[0] = p_sub_cc(F::P(0), a[0]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) t[i] = p_subc_cc(F::P(i), a[i]);
+  t[N - 1] = p_subc(F::P(N - 1), a[N - 1]);
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = nz ? t[i] : 0u;  // -0 = 0 stays canonical
+}
+
+// One Montgomery reduction round shared by every outer iteration:
+//   m = E[0] * (-p^-1) ; (E,O) += m * p   =>  E[0] becomes 0.
+// E holds limbs at positions 0..N-1, O holds limbs at positions 1..N.
+template <class F>
+B200_DEV void mont_round(uint32_t* E, uint32_t* O) {
+  constexpr int N = F::N;
+  const uint32_t m = E[0] * F::INV;
+  // odd-position products m*p[1], m*p[3], ... : one carry chain over O; the value is bounded so no carry-out
+  O[0] = p_mad_lo_cc(m, F::P(1), O[0]);
+  O[1] = p_madc_hi_cc(m, F::P(1), O[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    O[j] = p_madc_lo_cc(m, F::P(j + 1), O[j]);
+    O[j + 1] = p_madc_hi_cc(m, F::P(j + 1), O[j + 1]);
+  }
+  // even-position products: one carry chain over E; its carry-out lands on position N = O[N-1]
+  E[0] = p_mad_lo_cc(m, F::P(0), E[0]);
+  E[1] = p_madc_hi_cc(m, F::P(0), E[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    E[j] = p_madc_lo_cc(m, F::P(j), E[j]);
+    E[j + 1] = p_madc_hi_cc(m, F::P(j), E[j + 1]);
+  }
+  O[N - 1] = p_addc(O[N - 1], 0);
+}
+
+// Outer iteration i >= 1. On entry the running value is T = Eold + Oold*2^32 with Eold[0] == 0; the implied
+// division by 2^32 makes Oold the new position-0 row (`E`) and Eold >> 64 the new position-1 row (`O`, shifted
+// in place by two limbs), with the stray limb Eold[1] folded into E[0].
+template <class F>
+B200_DEV void mont_step(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi) {
+  constexpr int N = F::N;
+  E[0] = p_add_cc(E[0], O[1]);  // carry goes to position 1 = head of the O chain below
+#pragma unroll
+  for (int j = 0; j < N - 2; j += 2) {
+    O[j] = p_madc_lo_cc(a[j + 1], bi, O[j + 2]);
+    O[j + 1] = p_madc_hi_cc(a[j + 1], bi, O[j + 3]);
+  }
+  O[N - 2] = p_madc_lo_cc(a[N - 1], bi, 0);
+  O[N - 1] = p_madc_hi(a[N - 1], bi, 0);
+  E[0] = p_mad_lo_cc(a[0], bi, E[0]);
+  E[1] = p_madc_hi_cc(a[0], bi, E[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    E[j] = p_madc_lo_cc(a[j], bi, E[j]);
+    E[j + 1] = p_madc_hi_cc(a[j], bi, E[j + 1]);
+  }
+  O[N - 1] = p_addc(O[N - 1], 0);
+  mont_round<F>(E, O);
+}
+
+// r = a * b * R^-1 mod p, canonical.  a, b canonical (< p).   r may alias a or b.
+template <class F>
+B200_DEV void fe_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  constexpr int N = F::N;
+  static_assert(N % 2 == 0, "even limb count");
+  uint32_t A[N], B[N];
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+    A[j] = p_mul_lo(a[j], b[0]);
+    A[j + 1] = p_mul_hi(a[j], b[0]);
+    B[j] = p_mul_lo(a[j + 1], b[0]);
+    B[j + 1] = p_mul_hi(a[j + 1], b[0]);
+  }
+  mont_round<F>(A, B);
+#pragma unroll
+  for (int i = 1; i < N; i++) {
+    if (i & 1)
+      mont_step<F>(B, A, a, b[i]);
+    else
+      mont_step<F>(A, B, a, b[i]);
+  }
+  // N is even: after the last step (i = N-1, odd) the position-0 row is B, the position-1 row is A... and the
+  // final /2^32 gives  result = (row0 >> 32) + row1.
+  uint32_t* E = ((N - 1) & 1) ? B : A;
+  uint32_t* O = ((N - 1) & 1) ? A : B;
+  uint32_t t[N];
+  t[0] = p_add_cc(O[0], E[1]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) t[k] = p_addc_cc(O[k], E[k + 1]);
+  t[N - 1] = p_addc(O[N - 1], 0);
+  final_sub<F>(t);
+#pragma unroll
+  for (int k = 0; k < N; k++) r[k] = t[k];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Value types with a common interface (zero/one/is_zero/==, +, -, *, sqr, neg, dbl) so that the
+// elliptic-curve code is written once for G1 (Fp) and G2 (Fp2).
+// ---------------------------------------------------------------------------------------------------------
+template <class F>
+struct Fp {
+  using Params = F;
+  static constexpr int N = F::N;
+  static constexpr int WORDS = F::N;  // 32-bit words per element
+  uint32_t l[N];
+
+  B200_DEV static Fp zero() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.l[i] = 0;
+    return r;
+  }
+  B200_DEV static Fp one() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.l[i] = F::ONE(i);
+    return r;
+  }
+  B200_DEV bool is_zero() const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= l[i];
+    return o == 0;
+  }
+  B200_DEV bool operator==(const Fp& b) const {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= l[i] ^ b.l[i];
+    return o == 0;
+  }
+  B200_DEV Fp operator+(const Fp& b) const { Fp r; fe_add<F>(r.l, l, b.l); return r; }
+  B200_DEV Fp operator-(const Fp& b) const { Fp r; fe_sub<F>(r.l, l, b.l); return r; }
+  B200_DEV Fp operator*(const Fp& b) const { Fp r; fe_mul<F>(r.l, l, b.l); return r; }
+  B200_DEV Fp sqr() const { Fp r; fe_mul<F>(r.l, l, l); return r; }
+  B200_DEV Fp neg() const { Fp r; fe_neg<F>(r.l, l); return r; }
+  B200_DEV Fp dbl() const { Fp r; fe_add<F>(r.l, l, l); return r; }
+  // this = cond ? -this : this
+  B200_DEV void cneg(bool cond) {
+    Fp n = neg();
+#pragma unroll
+    for (int i = 0; i < N; i++) l[i] = cond ? n.l[i] : l[i];
+  }
+  // word-wise (de)serialisation used by the point loaders; k in [0, WORDS)
+  B200_DEV uint32_t word(int k) const { return l[k]; }
+  B200_DEV void set_word(int k, uint32_t v) { l[k] = v; }
+};
+
+// Fp2 = Fp[i] / (i^2 + 1)   (reference extension_fields/towers.nim:39-50: coords[0] + coords[1]*i)
+template <class F>
+struct Fp2 {
+  using Params = F;
+  using Base = Fp<F>;
+  static constexpr int N = F::N;
+  static constexpr int WORDS = 2 * F::N;
+  Base c0, c1;
+
+  B200_DEV static Fp2 zero() { Fp2 r; r.c0 = Base::zero(); r.c1 = Base::zero(); return r; }
+  B200_DEV static Fp2 one() { Fp2 r; r.c0 = Base::one(); r.c1 = Base::zero(); return r; }
+  B200_DEV bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+  B200_DEV bool operator==(const Fp2& b) const { return (c0 == b.c0) && (c1 == b.c1); }
+  B200_DEV Fp2 operator+(const Fp2& b) const { Fp2 r; r.c0 = c0 + b.c0; r.c1 = c1 + b.c1; return r; }
+  B200_DEV Fp2 operator-(const Fp2& b) const { Fp2 r; r.c0 = c0 - b.c0; r.c1 = c1 - b.c1; return r; }
+  B200_DEV Fp2 operator*(const Fp2& b) const {
+    // Karatsuba over i^2 = -1: 3 base multiplications
+    Base v0 = c0 * b.c0;
+    Base v1 = c1 * b.c1;
+    Base s = (c0 + c1) * (b.c0 + b.c1);
+    Fp2 r;
+    r.c0 = v0 - v1;
+    r.c1 = (s - v0) - v1;
+    return r;
+  }
+  B200_DEV Fp2 sqr() const {
+    // (a0+a1 i)^2 = (a0+a1)(a0-a1) + 2 a0 a1 i : 2 base multiplications
+    Base t = c0 * c1;
+    Fp2 r;
+    r.c0 = (c0 + c1) * (c0 - c1);
+    r.c1 = t + t;
+    return r;
+  }
+  B200_DEV Fp2 neg() const { Fp2 r; r.c0 = c0.neg(); r.c1 = c1.neg(); return r; }
+  B200_DEV Fp2 dbl() const { Fp2 r; r.c0 = c0.dbl(); r.c1 = c1.dbl(); return r; }
+  B200_DEV void cneg(bool cond) { c0.cneg(cond); c1.cneg(cond); }
+  B200_DEV uint32_t word(int k) const { return k < N ? c0.l[k] : c1.l[k - N]; }
+  B200_DEV void set_word(int k, uint32_t v) { if (k < N) c0.l[k] = v; else c1.l[k - N] = v; }
+};
+
+}  // namespace b200
