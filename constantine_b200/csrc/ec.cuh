@@ -130,6 +130,13 @@ B200_DEV Xyzz<T> xyzz_dbl(const Xyzz<T>& p) {
   return r;
 }
 
+// Out-of-line copies for the rare branches of the hot kernel and for every kernel that is not the hot one
+// (keeps ptxas time and code size bounded: each is compiled once per coordinate type instead of once per call site).
+template <class T>
+__device__ __noinline__ void xyzz_dbl_affine_ni(Xyzz<T>& r, const Aff<T>& p) { r = xyzz_dbl_affine(p); }
+template <class T>
+__device__ __noinline__ void xyzz_dbl_ni(Xyzz<T>& r) { r = xyzz_dbl(r); }
+
 // acc += q  (q affine, finite or infinity): madd-2008-s, 8M + 2S on the generic path.
 template <class T>
 B200_DEV void xyzz_madd(Xyzz<T>& acc, const Aff<T>& q) {
@@ -143,7 +150,7 @@ B200_DEV void xyzz_madd(Xyzz<T>& acc, const Aff<T>& q) {
   T P = U2 - acc.x;
   T R = S2 - acc.y;
   if (P.is_zero()) {
-    if (R.is_zero()) acc = xyzz_dbl_affine(q);
+    if (R.is_zero()) xyzz_dbl_affine_ni(acc, q);
     else acc = Xyzz<T>::inf();
     return;
   }
@@ -170,7 +177,7 @@ B200_DEV void xyzz_add(Xyzz<T>& acc, const Xyzz<T>& q) {
   T P = U2 - U1;
   T R = S2 - S1;
   if (P.is_zero()) {
-    if (R.is_zero()) acc = xyzz_dbl(acc);
+    if (R.is_zero()) xyzz_dbl_ni(acc);
     else acc = Xyzz<T>::inf();
     return;
   }
@@ -184,5 +191,12 @@ B200_DEV void xyzz_add(Xyzz<T>& acc, const Xyzz<T>& q) {
   acc.zz = acc.zz * q.zz * PP;
   acc.zzz = acc.zzz * q.zzz * PPP;
 }
+
+template <class T>
+__device__ __noinline__ void xyzz_add_ni(Xyzz<T>& acc, const Xyzz<T>& q) { xyzz_add(acc, q); }
+template <class T>
+__device__ __noinline__ void xyzz_madd_ni(Xyzz<T>& acc, const Aff<T>& q) { xyzz_madd(acc, q); }
+template <class T>
+__device__ __noinline__ void mul_ni(T& r, const T& a, const T& b) { r = a * b; }
 
 }  // namespace b200

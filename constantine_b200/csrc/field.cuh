@@ -244,6 +244,19 @@ struct Fp {
   // word-wise (de)serialisation used by the point loaders; k in [0, WORDS)
   B200_DEV uint32_t word(int k) const { return l[k]; }
   B200_DEV void set_word(int k, uint32_t v) { l[k] = v; }
+  // a^(p-2) (Fermat). Off the hot path only (affine normalisation in the input generator / test hooks).
+  __device__ __noinline__ Fp inv() const {
+    Fp r = one(), b = *this;
+#pragma unroll 1
+    for (int i = 0; i < 32 * N; i++) {
+      uint32_t w = F::P(i >> 5);
+      if ((i >> 5) == 0) w -= 2u;  // p is odd and its low word is > 2 for every field here
+      if ((w >> (i & 31)) & 1u) fe_mul_ni(r.l, r.l, b.l);
+      fe_mul_ni(b.l, b.l, b.l);
+    }
+    return r;
+  }
+  __device__ __noinline__ static void fe_mul_ni(uint32_t* r, const uint32_t* a, const uint32_t* b) { fe_mul<F>(r, a, b); }
 };
 
 // Fp2 = Fp[i] / (i^2 + 1)   (reference extension_fields/towers.nim:39-50: coords[0] + coords[1]*i)
@@ -282,6 +295,13 @@ struct Fp2 {
   B200_DEV Fp2 neg() const { Fp2 r; r.c0 = c0.neg(); r.c1 = c1.neg(); return r; }
   B200_DEV Fp2 dbl() const { Fp2 r; r.c0 = c0.dbl(); r.c1 = c1.dbl(); return r; }
   B200_DEV void cneg(bool cond) { c0.cneg(cond); c1.cneg(cond); }
+  __device__ __noinline__ Fp2 inv() const {
+    Base n = (c0.sqr() + c1.sqr()).inv();
+    Fp2 r;
+    r.c0 = c0 * n;
+    r.c1 = (c1 * n).neg();
+    return r;
+  }
   B200_DEV uint32_t word(int k) const { return k < N ? c0.l[k] : c1.l[k - N]; }
   B200_DEV void set_word(int k, uint32_t v) { if (k < N) c0.l[k] = v; else c1.l[k - N] = v; }
 };

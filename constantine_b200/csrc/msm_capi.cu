@@ -1,0 +1,180 @@
+// C ABI of libctt_b200_msm.so (declared in include/ctt_b200_msm.h; generated part: msm_capi_generated.inc).
+// extern "C", plain pointers and sizes only -- the same boundary the reference exports from
+// bindings/c_curve_decls_parallel.nim:31-45 (generated headers include/constantine/curves/*_parallel.h:21-24).
+#define CTT_B200_BUILDING_LIBRARY
+#include "../../include/ctt_b200_msm.h"
+#include "msm_hooks.cuh"
+#include <thread>
+
+namespace b200 {
+B200_DECLARE_CURVE(Bls12381G1) B200_DECLARE_CURVE(Bn254G1) B200_DECLARE_CURVE(PallasEc) B200_DECLARE_CURVE(VestaEc)
+B200_DECLARE_CURVE(Bls12381G2) B200_DECLARE_CURVE(Bn254G2)
+B200_DECLARE_FIELD(Bls12381Fp) B200_DECLARE_FIELD(Bn254SnarksFp) B200_DECLARE_FIELD(PallasFp) B200_DECLARE_FIELD(VestaFp)
+B200_DECLARE_FIELD(Bls12381Fr) B200_DECLARE_FIELD(Bn254SnarksFr) B200_DECLARE_FIELD(PallasFr) B200_DECLARE_FIELD(VestaFr)
+
+struct Bases {
+  int curve_id;
+  size_t len;
+  void* d_points;
+};
+}  // namespace b200
+
+#include "msm_capi_generated.inc"
+using namespace b200;
+
+extern "C" {
+
+struct ctt_threadpool { int num_threads; };
+
+// reference constantine/threadpool/threadpool.nim:943-973 (ctt_threadpool_new) -- here only a handle
+struct ctt_threadpool* ctt_threadpool_new(int num_threads) {
+  ctt_threadpool* tp = (ctt_threadpool*)malloc(sizeof(ctt_threadpool));
+  tp->num_threads = num_threads;
+  return tp;
+}
+// reference constantine/threadpool/threadpool.nim:1014-1041 (ctt_threadpool_shutdown)
+void ctt_threadpool_shutdown(struct ctt_threadpool* tp) { free(tp); }
+// reference include/constantine/core/threadpool.h:57
+int ctt_cpu_get_num_threads_os(void) { return (int)std::thread::hardware_concurrency(); }
+
+int ctt_b200_msm_device(int curve_id, int out_kind, void* r, const void* d_coefs, const void* d_points, size_t len,
+                        int fr_mont, int force_c, int win_begin, int win_end) {
+  switch (curve_id) {
+#define X(ID, DESC) case ID: msm_dev_ptrs<DESC>(r, d_coefs, d_points, len, fr_mont != 0, out_kind, force_c, win_begin, win_end); return 0;
+    B200_FOR_EACH_CURVE(X)
+#undef X
+  }
+  return -1;
+}
+
+int ctt_b200_msm_host(int curve_id, int out_kind, void* r, const void* coefs, const void* points, size_t len, int fr_mont) {
+  switch (curve_id) {
+#define X(ID, DESC) case ID: msm_host<DESC>(r, coefs, points, len, fr_mont != 0, out_kind); return 0;
+    B200_FOR_EACH_CURVE(X)
+#undef X
+  }
+  return -1;
+}
+
+int ctt_b200_sum_partials(int curve_id, int out_kind, void* r, const void* partials_xyzz, size_t count) {
+  switch (curve_id) {
+#define X(ID, DESC) case ID: return run_sum_partials<DESC>(out_kind, r, partials_xyzz, count);
+    B200_FOR_EACH_CURVE(X)
+#undef X
+  }
+  return -1;
+}
+
+int ctt_b200_plan(int curve_id, size_t len, int force_c, int* c, int* num_windows) {
+  int bits = 0;
+  switch (curve_id) {
+#define X(ID, DESC) case ID: bits = DESC::SCALAR_BITS; break;
+    B200_FOR_EACH_CURVE(X)
+#undef X
+    default: return -1;
+  }
+  Engine& E = engine();
+  int cc = force_c > 0 ? force_c : (E.tuning.force_c > 0 ? E.tuning.force_c : choose_window(len, bits));
+  if (cc < 2) cc = 2;
+  if (cc > 20) cc = 20;
+  *c = cc;
+  *num_windows = bits / cc + 1;
+  return 0;
+}
+
+ctt_b200_bases* ctt_b200_bases_upload(int curve_id, const void* points, size_t len) {
+  size_t coord = 0;
+  switch (curve_id) {
+#define X(ID, DESC) case ID: coord = DESC::COORD_BYTES; break;
+    B200_FOR_EACH_CURVE(X)
+#undef X
+    default: return nullptr;
+  }
+  Engine& E = engine();
+  std::lock_guard<std::mutex> lock(E.mu);
+  E.init();
+  Bases* b = new Bases;
+  b->curve_id = curve_id;
+  b->len = len;
+  B200_CUDA_CHECK(cudaMalloc(&b->d_points, len * 2 * coord + 16));
+  B200_CUDA_CHECK(cudaMemcpy(b->d_points, points, len * 2 * coord, cudaMemcpyHostToDevice));
+  return reinterpret_cast<ctt_b200_bases*>(b);
+}
+
+void ctt_b200_bases_free(ctt_b200_bases* bases) {
+  Bases* b = reinterpret_cast<Bases*>(bases);
+  if (!b) return;
+  cudaFree(b->d_points);
+  delete b;
+}
+
+int ctt_b200_msm_cached_bases(const ctt_b200_bases* bases, int out_kind, void* r, const void* coefs, size_t len, int fr_mont) {
+  const Bases* b = reinterpret_cast<const Bases*>(bases);
+  if (!b || len > b->len) return -1;
+  Engine& E = engine();
+  {
+    std::lock_guard<std::mutex> lock(E.mu);
+    E.init();
+    E.d_scalars.ensure(len * 32 + 16);
+    B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, len * 32, cudaMemcpyHostToDevice, E.stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(E.stream));
+  }
+  return ctt_b200_msm_device(b->curve_id, out_kind, r, E.d_scalars.ptr, b->d_points, len, fr_mont, 0, 0, -1);
+}
+
+void ctt_b200_last_stats(ctt_b200_stats* out) {
+  Engine& E = engine();
+  std::lock_guard<std::mutex> lock(E.mu);
+  static_assert(sizeof(ctt_b200_stats) == sizeof(Stats), "stats layout");
+  memcpy(out, &E.stats, sizeof(Stats));
+}
+
+void ctt_b200_set_tuning(int force_c, int reduce_chunk, int sum_group) {
+  Engine& E = engine();
+  std::lock_guard<std::mutex> lock(E.mu);
+  if (force_c > 0) E.tuning.force_c = force_c;
+  if (force_c < 0) E.tuning.force_c = 0;
+  if (reduce_chunk > 0) E.tuning.reduce_chunk = reduce_chunk;
+  if (sum_group > 0) E.tuning.sum_group = sum_group;
+}
+
+int ctt_b200_sm_count(void) {
+  Engine& E = engine();
+  std::lock_guard<std::mutex> lock(E.mu);
+  E.init();
+  return E.sm_count;
+}
+
+int ctt_b200_test_field_op(int field_id, int op, void* r, const void* a, const void* b, size_t count) {
+  switch (field_id) {
+    case 0: return run_test_field_op<Bls12381Fp>(op, r, a, b, count);
+    case 1: return run_test_field_op<Bn254SnarksFp>(op, r, a, b, count);
+    case 2: return run_test_field_op<PallasFp>(op, r, a, b, count);
+    case 3: return run_test_field_op<VestaFp>(op, r, a, b, count);
+    case 4: return run_test_field_op<Bls12381Fr>(op, r, a, b, count);
+    case 5: return run_test_field_op<Bn254SnarksFr>(op, r, a, b, count);
+    case 6: return run_test_field_op<PallasFr>(op, r, a, b, count);
+    case 7: return run_test_field_op<VestaFr>(op, r, a, b, count);
+  }
+  return -1;
+}
+
+int ctt_b200_scalar_mul_u64(int curve_id, const void* base_aff, const uint64_t* k, size_t count, void* out_aff) {
+  switch (curve_id) {
+#define X(ID, DESC) case ID: return run_scalar_mul_u64<DESC>(base_aff, k, count, out_aff);
+    B200_FOR_EACH_CURVE(X)
+#undef X
+  }
+  return -1;
+}
+
+int ctt_b200_test_ec_op(int curve_id, int op, void* r_xyzz, const void* p_aff, const void* q_aff, size_t count) {
+  switch (curve_id) {
+#define X(ID, DESC) case ID: return run_test_ec_op<DESC>(op, r_xyzz, p_aff, q_aff, count);
+    B200_FOR_EACH_CURVE(X)
+#undef X
+  }
+  return -1;
+}
+
+}  // extern "C"

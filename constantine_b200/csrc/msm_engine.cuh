@@ -1,0 +1,359 @@
+// Host-side engine: device context, scratch memory, the launch sequence of one MSM, and the serial host tail.
+// One engine per process and device (one process per GPU under torch.distributed); calls are serialised by a mutex
+// so the C ABI is re-entrant and thread-safe like the reference's (SURVEY.md section 8b "Threading").
+#pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include "msm_kernels.cuh"
+#include "host_field.hpp"
+
+namespace b200 {
+
+#define B200_CUDA_CHECK(expr)                                                                              \
+  do {                                                                                                     \
+    cudaError_t e__ = (expr);                                                                              \
+    if (e__ != cudaSuccess) {                                                                              \
+      fprintf(stderr, "[ctt_b200_msm] FATAL CUDA error %s (%s) at %s:%d -- no CPU fallback exists\n",      \
+              cudaGetErrorName(e__), cudaGetErrorString(e__), __FILE__, __LINE__);                         \
+      abort();                                                                                             \
+    }                                                                                                      \
+  } while (0)
+
+// ---- curve descriptors -------------------------------------------------------------------------------------
+template <class FpP, class FrP, int EXT>
+struct CurveDesc;
+template <class FpP, class FrP>
+struct CurveDesc<FpP, FrP, 1> {
+  using T = Fp<FpP>;                 // device coordinate type
+  using H = host::HFp<FpP>;          // host coordinate type
+  using FrParams = FrP;
+  static constexpr int SCALAR_BITS = FrP::BITS;
+  static constexpr int COORD_BYTES = FpP::N64 * 8;
+};
+template <class FpP, class FrP>
+struct CurveDesc<FpP, FrP, 2> {
+  using T = Fp2<FpP>;
+  using H = host::HFp2<FpP>;
+  using FrParams = FrP;
+  static constexpr int SCALAR_BITS = FrP::BITS;
+  static constexpr int COORD_BYTES = 2 * FpP::N64 * 8;
+};
+
+using Bls12381G1 = CurveDesc<Bls12381Fp, Bls12381Fr, 1>;
+using Bn254G1 = CurveDesc<Bn254SnarksFp, Bn254SnarksFr, 1>;
+using PallasEc = CurveDesc<PallasFp, PallasFr, 1>;
+using VestaEc = CurveDesc<VestaFp, VestaFr, 1>;
+using Bls12381G2 = CurveDesc<Bls12381Fp, Bls12381Fr, 2>;
+using Bn254G2 = CurveDesc<Bn254SnarksFp, Bn254SnarksFr, 2>;
+
+// ---- tunables (overridable through ctt_b200_set_tuning / environment, see msm_capi.cu) ---------------------
+struct Tuning {
+  int force_c = 0;            // 0 = cost model
+  int reduce_chunk = 16;      // L: buckets per bucket-reduce thread
+  int sum_group = 16;         // G: fan-in of the tree sum
+};
+
+struct Stats {               // filled per call; read back through ctt_b200_last_stats
+  int c = 0, num_windows = 0;
+  unsigned long long entries = 0;       // sorted (key,val) pairs
+  unsigned long long total_buckets = 0;
+  int kernel_launches = 0;              // kernels launched by the last call (ours + the radix sort's)
+  float ms_h2d = 0, ms_digits = 0, ms_sort = 0, ms_accumulate = 0, ms_fixup = 0, ms_reduce = 0, ms_d2h_tail = 0, ms_total = 0;
+};
+
+// Window size: minimise  W*N*MADD + W*2^(c-1)*REDUCE  (same shape as the reference's bestBucketBitSize cost,
+// reference ec_multi_scalar_mul_scheduler.nim:172-223, with GPU weights: bucket reduction is ~2.6 XYZZ adds of 14 mults
+// per bucket against 10 mults per accumulated point, and a floor on the number of slices so small inputs still
+// spread over the SMs).
+inline int choose_window(size_t n, int bits, int num_devices_windows = 1) {
+  double best = 1e300;
+  int best_c = 2;
+  for (int c = 2; c <= 20; c++) {
+    int W = bits / c + 1;
+    double acc = (double)W * (double)n * 10.0;
+    double red = (double)W * (double)(1u << (c - 1)) * 40.0;
+    double cost = acc + red;
+    if (cost < best) { best = cost; best_c = c; }
+  }
+  (void)num_devices_windows;
+  return best_c;
+}
+
+inline DigitPlan make_plan(int bits, int c, int win_begin = 0, int win_end = -1) {
+  DigitPlan p;
+  p.bits = bits; p.c = c;
+  p.num_full = bits / c;
+  p.num_windows = p.num_full + 1;
+  p.excess = bits % c;
+  p.top = bits - p.excess;
+  p.buckets_per_window = 1u << (c - 1);
+  p.total_buckets = (uint32_t)p.num_windows * p.buckets_per_window;
+  p.win_begin = win_begin;
+  p.win_end = (win_end < 0) ? p.num_windows : win_end;
+  return p;
+}
+
+// ---- device context ----------------------------------------------------------------------------------------
+struct DeviceBuffer {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  void ensure(size_t bytes) {
+    if (bytes <= cap) return;
+    if (ptr) B200_CUDA_CHECK(cudaFree(ptr));
+    size_t want = bytes + bytes / 8 + 256;
+    B200_CUDA_CHECK(cudaMalloc(&ptr, want));
+    cap = want;
+  }
+  void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+};
+
+struct Engine {
+  std::mutex mu;
+  bool ready = false;
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev[10];
+  cudaEvent_t ev_points_ready;
+  DeviceBuffer d_scalars, d_points, keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_pts[2], part_keys[2], red_a, red_b;
+  void* h_result = nullptr;   // pinned
+  size_t h_result_cap = 0;
+  Tuning tuning;
+  Stats stats;
+  bool collect_timing = true;
+
+  void init() {
+    if (ready) return;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+      fprintf(stderr, "[ctt_b200_msm] FATAL: no CUDA device available (%s). This library has no CPU fallback.\n",
+              cudaGetErrorString(e));
+      abort();
+    }
+    B200_CUDA_CHECK(cudaGetDevice(&device));
+    cudaDeviceProp prop;
+    B200_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    sm_count = prop.multiProcessorCount;
+    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    for (auto& x : ev) B200_CUDA_CHECK(cudaEventCreate(&x));
+    B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_points_ready, cudaEventDisableTiming));
+    h_result_cap = 1 << 20;
+    B200_CUDA_CHECK(cudaMallocHost(&h_result, h_result_cap));
+    ready = true;
+  }
+};
+
+inline Engine& engine() {
+  static Engine e;
+  return e;
+}
+
+// ---- one MSM on device-resident inputs ------------------------------------------------------------------------
+// d_scalars: n x 32 B, d_points: n affine points (ABI layout, Montgomery residues). Produces the window sums in pinned
+// host memory and runs the host tail. Window range [win_begin, win_end) lets several devices split one MSM by windows;
+// the returned point is then  sum_{w in range} 2^(c*w) * S_w.
+template <class C>
+host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const void* d_points, size_t n, bool fr_mont,
+                                      int force_c, int win_begin, int win_end, cudaEvent_t wait_points = nullptr) {
+  using T = typename C::T;
+  using H = typename C::H;
+  using HP = host::HXyzz<H>;
+  constexpr int KACC = 32;   // level-0 slice length
+  constexpr int KFIX = 8;    // fix-up slice length
+  Stats& st = E.stats;
+  int launches = 0;
+  if (n == 0) return HP::inf();
+  if (n >= (1ull << 31)) { fprintf(stderr, "[ctt_b200_msm] FATAL: len >= 2^31 unsupported\n"); abort(); }
+
+  int c = force_c > 0 ? force_c : (E.tuning.force_c > 0 ? E.tuning.force_c : choose_window(n, C::SCALAR_BITS));
+  if (c < 2) c = 2;
+  if (c > 20) c = 20;
+  DigitPlan plan = make_plan(C::SCALAR_BITS, c, win_begin, win_end);
+  const int nw = plan.win_end - plan.win_begin;
+  if (nw <= 0) return HP::inf();
+  const size_t entries = (size_t)nw * n;
+  const uint32_t B = plan.buckets_per_window;
+  const size_t nbuckets = (size_t)nw * B;
+  const uint32_t no_key = (uint32_t)nbuckets;
+  constexpr size_t XYZZ_BYTES = 4 * T::WORDS * 4;
+  st.c = c; st.num_windows = nw; st.entries = entries; st.total_buckets = nbuckets;
+
+  cudaStream_t s = E.stream;
+  E.keys_a.ensure(entries * 4); E.keys_b.ensure(entries * 4);
+  E.vals_a.ensure(entries * 4); E.vals_b.ensure(entries * 4);
+  E.buckets.ensure(nbuckets * XYZZ_BYTES);
+  const size_t slices0 = (entries + KACC - 1) / KACC;
+  E.part_pts[0].ensure(slices0 * XYZZ_BYTES); E.part_keys[0].ensure(slices0 * 4);
+  const size_t slices1 = (slices0 + KFIX - 1) / KFIX;
+  E.part_pts[1].ensure(slices1 * XYZZ_BYTES); E.part_keys[1].ensure(slices1 * 4);
+
+  if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[0], s));
+  // 1. digits
+  {
+    dim3 grid((unsigned)((n + 255) / 256)), block(256);
+    if (fr_mont)
+      k_digits<typename C::FrParams, true><<<grid, block, 0, s>>>((const uint32_t*)d_scalars, (uint32_t)n, plan, (uint32_t*)E.keys_a.ptr, (uint32_t*)E.vals_a.ptr);
+    else
+      k_digits<typename C::FrParams, false><<<grid, block, 0, s>>>((const uint32_t*)d_scalars, (uint32_t)n, plan, (uint32_t*)E.keys_a.ptr, (uint32_t*)E.vals_a.ptr);
+    launches++;
+  }
+  if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[1], s));
+  // 2. sort by key
+  int end_bit = 1;
+  while ((1ull << end_bit) <= (unsigned long long)no_key) end_bit++;
+  cub::DoubleBuffer<uint32_t> dk((uint32_t*)E.keys_a.ptr, (uint32_t*)E.keys_b.ptr);
+  cub::DoubleBuffer<uint32_t> dv((uint32_t*)E.vals_a.ptr, (uint32_t*)E.vals_b.ptr);
+  {
+    size_t tmp_bytes = 0;
+    B200_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int64_t)entries, 0, end_bit, s));
+    E.cub_tmp.ensure(tmp_bytes);
+    B200_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(E.cub_tmp.ptr, tmp_bytes, dk, dv, (int64_t)entries, 0, end_bit, s));
+    launches += 2 + (end_bit + 7) / 8;  // histogram + exclusive-sum + one onesweep pass per 8 key bits
+  }
+  const uint32_t* keys = dk.Current();
+  const uint32_t* vals = dv.Current();
+  B200_CUDA_CHECK(cudaMemsetAsync(E.buckets.ptr, 0, nbuckets * XYZZ_BYTES, s));  // all-zero XYZZ = infinity
+  if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[2], s));
+  // 3. accumulate
+  if (wait_points) B200_CUDA_CHECK(cudaStreamWaitEvent(s, wait_points, 0));
+  {
+    dim3 block(128), grid((unsigned)((slices0 + 127) / 128));
+    k_accumulate<T, KACC><<<grid, block, 0, s>>>(keys, vals, entries, no_key, (const uint32_t*)d_points, (uint32_t*)E.buckets.ptr,
+                                                 (uint32_t*)E.part_pts[0].ptr, (uint32_t*)E.part_keys[0].ptr, slices0);
+    launches++;
+  }
+  if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[3], s));
+  // 4. fix-up levels
+  {
+    size_t count = slices0;
+    int cur = 0;
+    while (count > 1) {
+      size_t ns = (count + KFIX - 1) / KFIX;
+      dim3 block(128), grid((unsigned)((ns + 127) / 128));
+      k_fixup<T, KFIX><<<grid, block, 0, s>>>((const uint32_t*)E.part_keys[cur].ptr, (const uint32_t*)E.part_pts[cur].ptr, count,
+                                              (uint32_t*)E.buckets.ptr, (uint32_t*)E.part_pts[cur ^ 1].ptr, (uint32_t*)E.part_keys[cur ^ 1].ptr, ns);
+      launches++;
+      count = ns;
+      cur ^= 1;
+    }
+    // a single remaining slice never continues a previous one: its runs were all added to their buckets.
+  }
+  if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[4], s));
+  // 5. bucket reduce + tree sum
+  uint32_t L = (uint32_t)E.tuning.reduce_chunk;
+  if (L < 1) L = 1;
+  uint32_t chunks = (B + L - 1) / L;
+  // keep at least ~8 warps per SM worth of chunk threads when the bucket count allows it
+  while (L > 1 && (size_t)chunks * nw < (size_t)E.sm_count * 256 && chunks < B) { L = (L + 1) / 2; chunks = (B + L - 1) / L; }
+  E.red_a.ensure((size_t)chunks * nw * XYZZ_BYTES);
+  {
+    size_t threads = (size_t)chunks * nw;
+    dim3 block(128), grid((unsigned)((threads + 127) / 128));
+    k_bucket_reduce<T><<<grid, block, 0, s>>>((const uint32_t*)E.buckets.ptr, B, L, chunks, (uint32_t)nw, (uint32_t*)E.red_a.ptr);
+    launches++;
+  }
+  uint32_t row = chunks;
+  const uint32_t G = (uint32_t)(E.tuning.sum_group < 2 ? 2 : E.tuning.sum_group);
+  DeviceBuffer* src = &E.red_a;
+  DeviceBuffer* dst = &E.red_b;
+  while (row > 1) {
+    uint32_t out_row = (row + G - 1) / G;
+    dst->ensure((size_t)out_row * nw * XYZZ_BYTES);
+    size_t threads = (size_t)out_row * nw;
+    dim3 block(128), grid((unsigned)((threads + 127) / 128));
+    k_sum_groups<T><<<grid, block, 0, s>>>((const uint32_t*)src->ptr, row, G, out_row, (uint32_t)nw, (uint32_t*)dst->ptr);
+    launches++;
+    row = out_row;
+    DeviceBuffer* tmp = src; src = dst; dst = tmp;
+  }
+  if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[5], s));
+  // 6. window sums -> host, Horner tail
+  const size_t out_bytes = (size_t)nw * XYZZ_BYTES;
+  if (out_bytes > E.h_result_cap) { fprintf(stderr, "[ctt_b200_msm] FATAL: result staging too small\n"); abort(); }
+  B200_CUDA_CHECK(cudaMemcpyAsync(E.h_result, src->ptr, out_bytes, cudaMemcpyDeviceToHost, s));
+  B200_CUDA_CHECK(cudaStreamSynchronize(s));
+  static_assert(sizeof(HP) == XYZZ_BYTES, "host/device XYZZ layout");
+  const HP* sums = reinterpret_cast<const HP*>(E.h_result);
+  // r = sum_w 2^(c*w) S_w  for w in [win_begin, win_end):  Horner from the top window of the range, then shift by c*win_begin
+  // (reference ec_multi_scalar_mul_parallel.nim:198-203: c doublings + one addition per window).
+  HP r = sums[nw - 1];
+  for (int w = nw - 2; w >= 0; w--) {
+    for (int i = 0; i < c; i++) r = host::xyzz_dbl(r);
+    r = host::xyzz_add(r, sums[w]);
+  }
+  for (int i = 0; i < c * plan.win_begin; i++) r = host::xyzz_dbl(r);
+  if (E.collect_timing) {
+    B200_CUDA_CHECK(cudaEventRecord(E.ev[6], s));
+    B200_CUDA_CHECK(cudaEventSynchronize(E.ev[6]));
+    cudaEventElapsedTime(&st.ms_digits, E.ev[0], E.ev[1]);
+    cudaEventElapsedTime(&st.ms_sort, E.ev[1], E.ev[2]);
+    cudaEventElapsedTime(&st.ms_accumulate, E.ev[2], E.ev[3]);
+    cudaEventElapsedTime(&st.ms_fixup, E.ev[3], E.ev[4]);
+    cudaEventElapsedTime(&st.ms_reduce, E.ev[4], E.ev[5]);
+    cudaEventElapsedTime(&st.ms_d2h_tail, E.ev[5], E.ev[6]);
+    cudaEventElapsedTime(&st.ms_total, E.ev[0], E.ev[6]);
+  }
+  st.kernel_launches = launches;
+  return r;
+}
+
+// ---- result conversion ------------------------------------------------------------------------------------------
+enum OutKind { OUT_JAC = 0, OUT_PRJ = 1 };
+
+template <class C>
+void write_result(void* r_out, const host::HXyzz<typename C::H>& p, int kind) {
+  using H = typename C::H;
+  H X, Y, Z;
+  if (kind == OUT_JAC) host::xyzz_to_jac(p, X, Y, Z);
+  else host::xyzz_to_prj(p, X, Y, Z);
+  char* o = (char*)r_out;
+  memcpy(o, &X, sizeof(H));
+  memcpy(o + sizeof(H), &Y, sizeof(H));
+  memcpy(o + 2 * sizeof(H), &Z, sizeof(H));
+}
+
+// ---- host-pointer entry (the reference's C ABI semantics): copy in, run, convert ----------------------------------
+template <class C>
+void msm_host(void* r_out, const void* coefs, const void* points, size_t len, bool fr_mont, int kind) {
+  Engine& E = engine();
+  std::lock_guard<std::mutex> lock(E.mu);
+  E.init();
+  using HP = host::HXyzz<typename C::H>;
+  if (len == 0) { write_result<C>(r_out, HP::inf(), kind); return; }  // upstream: UB; here: neutral element
+  const size_t sbytes = len * 32, pbytes = len * (size_t)(2 * C::COORD_BYTES);
+  E.d_scalars.ensure(sbytes);
+  E.d_points.ensure(pbytes);
+  cudaEvent_t t0 = E.ev[7], t1 = E.ev[8];
+  B200_CUDA_CHECK(cudaEventRecord(t0, E.stream));
+  // scalars on the compute stream (digits + sort need only them); points on the copy stream so that the transfer
+  // overlaps digit extraction and sorting.
+  B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, sbytes, cudaMemcpyHostToDevice, E.stream));
+  B200_CUDA_CHECK(cudaMemcpyAsync(E.d_points.ptr, points, pbytes, cudaMemcpyHostToDevice, E.copy_stream));
+  B200_CUDA_CHECK(cudaEventRecord(E.ev_points_ready, E.copy_stream));
+  B200_CUDA_CHECK(cudaEventRecord(t1, E.stream));
+  HP r = msm_device<C>(E, E.d_scalars.ptr, E.d_points.ptr, len, fr_mont, 0, 0, -1, E.ev_points_ready);
+  if (E.collect_timing) cudaEventElapsedTime(&E.stats.ms_h2d, t0, t1);
+  write_result<C>(r_out, r, kind);
+}
+
+// device-pointer entry (inputs already resident in HBM; used by bench.py `value` and by the cached-bases API)
+template <class C>
+void msm_dev_ptrs(void* r_out, const void* d_coefs, const void* d_points, size_t len, bool fr_mont, int kind, int force_c,
+                  int win_begin, int win_end) {
+  Engine& E = engine();
+  std::lock_guard<std::mutex> lock(E.mu);
+  E.init();
+  using HP = host::HXyzz<typename C::H>;
+  HP r = msm_device<C>(E, d_coefs, d_points, len, fr_mont, force_c, win_begin, win_end);
+  if (kind == 2) memcpy(r_out, &r, sizeof(HP));  // raw XYZZ (for multi-GPU partial combination)
+  else write_result<C>(r_out, r, kind);
+}
+
+}  // namespace b200

@@ -1,0 +1,227 @@
+// Pippenger bucket-method kernels for one B200 (sm_100a), generic over the curve.
+//
+// What this replaces on the reference's hot path:
+//   a10  signed Booth window extraction      reference constantine/math/arithmetic/bigints.nim:360-379, 806-861
+//   a7   bucket accumulation + reduction     reference constantine/math/elliptic/ec_multi_scalar_mul.nim:177-235
+//   a5/a6 one-task-per-window decomposition  reference constantine/math/elliptic/ec_multi_scalar_mul_parallel.nim:148-208, 316-431
+//   a2   Fr (Montgomery) -> canonical scalars reference constantine/math/elliptic/ec_multi_scalar_mul_parallel.nim:611-628
+//
+// B200 mapping (DESIGN.md has the full data-flow):
+//   1. k_digits        one thread per scalar: all W signed digits -> (key = window*B + bucket, val = point index | sign<<31)
+//   2. radix sort       (key,val) pairs by key; zero digits carry the key W*B and sort to the tail
+//   3. k_accumulate    the sorted list is cut into fixed slices of K entries, one thread per slice; a thread sums the
+//                      points of each run of equal keys in registers (XYZZ mixed adds). Runs that start inside the slice
+//                      own their bucket and store it; a run that continues from the previous slice is emitted as a
+//                      "partial" -- perfectly load-balanced whatever the digit distribution is.
+//   4. k_fixup         the partials form a (much shorter) sorted list themselves: same slicing, XYZZ+XYZZ adds, added
+//                      into the owning bucket; repeated until a level has a single slice.
+//   5. k_bucket_reduce per window, T threads x L consecutive buckets: running sum + (t*L)*run offset, then k_sum_groups
+//                      tree-sums the T partial results -> one point per window.
+//   6. host tail       Horner over the <= W window sums (host_field.hpp).
+#pragma once
+#include "ec.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------- digits
+struct DigitPlan {
+  int bits;        // declared scalar width b (254 / 255)
+  int c;           // window size
+  int num_full;    // b / c
+  int num_windows; // num_full + 1   (reference parallel.nim:157-158: the recoding must see one more window)
+  int excess;      // b % c
+  int top;         // b - excess
+  uint32_t buckets_per_window;  // 2^(c-1)
+  uint32_t total_buckets;       // num_windows * 2^(c-1); also the key of "no bucket" (zero digit)
+  int win_begin, win_end;       // windows handled by this device (multi-GPU window sharding), [begin, end)
+};
+
+__device__ __forceinline__ uint32_t scalar_window(const uint32_t* k, int bit_index, int nbits) {
+  // bits [bit_index, bit_index + nbits) of the 256-bit little-endian scalar; bits >= 256 read as zero
+  // (reference bigints.nim:360-379 getWindowAt: the next limb is only read if it exists). nbits <= 24.
+  int word = bit_index >> 5, pos = bit_index & 31;
+  uint64_t lo = (word < 8) ? k[word] : 0u;
+  uint64_t hi = (word + 1 < 8) ? k[word + 1] : 0u;
+  uint64_t v = (lo | (hi << 32)) >> pos;
+  return (uint32_t)v & ((1u << nbits) - 1u);
+}
+
+// Booth recoding of a (bitsize+1)-bit digit (reference bigints.nim:806-832 signedWindowEncoding)
+__device__ __forceinline__ void signed_encode(uint32_t digit, int bitsize, uint32_t& val, uint32_t& neg) {
+  neg = digit >> bitsize;
+  uint32_t mask = 0u - neg;
+  uint32_t enc = (digit + 1u) >> 1;
+  val = ((enc + mask) ^ mask) & ((1u << bitsize) - 1u);
+}
+
+// digit of window w under plan p (reference bigints.nim:834-861; window kinds per parallel.nim:171-196)
+__device__ __forceinline__ void window_digit(const uint32_t* k, const DigitPlan& p, int w, uint32_t& val, uint32_t& neg) {
+  if (w == p.num_full) {
+    if (p.top == 0) signed_encode(scalar_window(k, 0, p.c) << 1, p.c, val, neg);
+    else if (p.excess == 0) signed_encode(scalar_window(k, p.top - 1, p.c + 1), p.c, val, neg);
+    else signed_encode(scalar_window(k, p.top - 1, p.excess + 1), p.excess + 1, val, neg);
+  } else if (w == 0) {
+    signed_encode(scalar_window(k, 0, p.c) << 1, p.c, val, neg);
+  } else {
+    signed_encode(scalar_window(k, w * p.c - 1, p.c + 1), p.c, val, neg);
+  }
+}
+
+// One thread per scalar. FR_MONT: scalars arrive as Fr Montgomery residues and are first converted to canonical
+// integers by one Montgomery reduction (multiplication by the integer 1), like the reference's fromField pass.
+template <class FrParams, bool FR_MONT>
+__global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ scalars, uint32_t n, DigitPlan plan,
+                                                uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k[8];
+  const uint4* src = reinterpret_cast<const uint4*>(scalars) + (size_t)i * 2;
+  uint4 a = __ldg(src), b = __ldg(src + 1);
+  k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
+  if (FR_MONT) {
+    static_assert(FrParams::N == 8, "256-bit scalar fields");
+    uint32_t one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+    fe_mul<FrParams>(k, k, one);
+  }
+  const int nw = plan.win_end - plan.win_begin;
+  for (int w = plan.win_begin; w < plan.win_end; w++) {
+    uint32_t val, neg;
+    window_digit(k, plan, w, val, neg);
+    size_t slot = (size_t)(w - plan.win_begin) * n + i;
+    keys[slot] = val ? (uint32_t)(w - plan.win_begin) * plan.buckets_per_window + (val - 1u) : (uint32_t)nw * plan.buckets_per_window;
+    vals[slot] = i | (neg << 31);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- bucket accumulation
+constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
+
+// Slice kernel over the sorted (key, point-ref) list.  `no_key` = first key value that means "no bucket".
+template <class T, int K>
+__global__ void __launch_bounds__(128) k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                    size_t total, uint32_t no_key, const uint32_t* __restrict__ points,
+                                                    uint32_t* buckets, uint32_t* part_pts, uint32_t* part_keys, size_t num_slices) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= num_slices) return;
+  size_t base = t * K;
+  uint32_t prev_key = (t > 0) ? keys[base - 1] : KEY_NONE;
+  uint32_t cur_key = KEY_NONE;
+  bool wrote_partial = false;
+  Xyzz<T> acc = Xyzz<T>::inf();
+#pragma unroll 1
+  for (int j = 0; j < K; j++) {
+    size_t idx = base + j;
+    if (idx >= total) break;
+    uint32_t key = keys[idx];
+    if (key >= no_key) break;  // zero digits are sorted to the tail: nothing left in this slice
+    uint32_t v = vals[idx];
+    Aff<T> p = load_affine<T>(points, v & 0x7FFFFFFFu);
+    if (!p.is_inf()) p.y.cneg((v >> 31) != 0);
+    if (key != cur_key) {
+      if (cur_key != KEY_NONE) {
+        if (cur_key == prev_key) { store_xyzz(part_pts, t, acc); part_keys[t] = cur_key; wrote_partial = true; }
+        else store_xyzz(buckets, (size_t)cur_key, acc);
+      }
+      cur_key = key;
+      acc = Xyzz<T>::from_affine(p);
+    } else {
+      xyzz_madd(acc, p);
+    }
+  }
+  if (cur_key != KEY_NONE) {
+    if (cur_key == prev_key) { store_xyzz(part_pts, t, acc); part_keys[t] = cur_key; wrote_partial = true; }
+    else store_xyzz(buckets, (size_t)cur_key, acc);
+  }
+  if (!wrote_partial) part_keys[t] = KEY_NONE;
+}
+
+// Fix-up level: input = list of (key, XYZZ) partials in slice order (KEY_NONE entries are holes).  Equal keys are
+// contiguous.  Same slicing; a run continuing from the previous slice is forwarded to the next level, every other
+// run is added into its bucket (exactly one thread per key and level does so).
+template <class T, int K>
+__global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ in_keys, const uint32_t* in_pts, size_t count,
+                                               uint32_t* buckets, uint32_t* out_pts, uint32_t* out_keys, size_t num_slices) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= num_slices) return;
+  size_t base = t * K;
+  uint32_t prev_key = (t > 0) ? in_keys[base - 1] : KEY_NONE;
+  uint32_t cur_key = KEY_NONE;
+  bool wrote_partial = false;
+  Xyzz<T> acc = Xyzz<T>::inf();
+#pragma unroll 1
+  for (int j = 0; j < K; j++) {
+    size_t idx = base + j;
+    if (idx >= count) break;
+    uint32_t key = in_keys[idx];
+    if (key != cur_key) {
+      if (cur_key != KEY_NONE) {
+        if (cur_key == prev_key) { store_xyzz(out_pts, t, acc); out_keys[t] = cur_key; wrote_partial = true; }
+        else { Xyzz<T> b = load_xyzz<T>(buckets, (size_t)cur_key); xyzz_add_ni(b, acc); store_xyzz(buckets, (size_t)cur_key, b); }
+      }
+      cur_key = key;
+      if (key != KEY_NONE) acc = load_xyzz<T>(in_pts, idx);
+    } else if (key != KEY_NONE) {
+      Xyzz<T> q = load_xyzz<T>(in_pts, idx);
+      xyzz_add_ni(acc, q);
+    }
+  }
+  if (cur_key != KEY_NONE) {
+    if (cur_key == prev_key) { store_xyzz(out_pts, t, acc); out_keys[t] = cur_key; wrote_partial = true; }
+    else { Xyzz<T> b = load_xyzz<T>(buckets, (size_t)cur_key); xyzz_add_ni(b, acc); store_xyzz(buckets, (size_t)cur_key, b); }
+  }
+  if (!wrote_partial) out_keys[t] = KEY_NONE;
+}
+
+// ------------------------------------------------------------------------------------------- bucket reduction
+// Window sum  S = sum_{j=0}^{B-1} (j+1) * bucket[j]   (reference ec_multi_scalar_mul.nim:186-197 bucketReduce computes
+// the same value with one serial running sum).  Here B buckets are cut into T = B/L chunks of L consecutive buckets:
+//   chunk t:  run = sum_i b[tL+i],  acc = sum_i (i+1) b[tL+i]  (running sum, 2 adds per bucket)
+//   S = sum_t ( acc_t + (t*L) * run_t )
+// (t*L)*run_t is a <= 20-bit double-and-add.  Output: one point per chunk; k_sum_groups adds them up.
+template <class T>
+__global__ void __launch_bounds__(128) k_bucket_reduce(const uint32_t* buckets, uint32_t buckets_per_window, uint32_t L,
+                                                       uint32_t chunks_per_window, uint32_t num_windows, uint32_t* out) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (size_t)chunks_per_window * num_windows) return;
+  uint32_t w = (uint32_t)(g / chunks_per_window), t = (uint32_t)(g % chunks_per_window);
+  size_t first = (size_t)w * buckets_per_window + (size_t)t * L;
+  uint32_t cnt = min(L, buckets_per_window - t * L);
+  Xyzz<T> run = Xyzz<T>::inf(), acc = Xyzz<T>::inf();
+#pragma unroll 1
+  for (int i = (int)cnt - 1; i >= 0; i--) {
+    Xyzz<T> b = load_xyzz<T>(buckets, first + i);
+    xyzz_add_ni(run, b);
+    xyzz_add_ni(acc, run);
+  }
+  uint32_t off = t * L;
+  if (off != 0 && !run.is_inf()) {
+    Xyzz<T> m = Xyzz<T>::inf();
+#pragma unroll 1
+    for (int bit = 31 - __clz(off); bit >= 0; bit--) {
+      xyzz_dbl_ni(m);
+      if ((off >> bit) & 1u) xyzz_add_ni(m, run);
+    }
+    xyzz_add_ni(acc, m);
+  }
+  store_xyzz(out, g, acc);
+}
+
+// out[g] = sum_{i < G} in[g*G + i]  within each window's row of `row_len` entries (rows are padded to groups)
+template <class T>
+__global__ void __launch_bounds__(128) k_sum_groups(const uint32_t* in, uint32_t row_len, uint32_t G, uint32_t out_row_len,
+                                                    uint32_t num_rows, uint32_t* out) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (size_t)out_row_len * num_rows) return;
+  uint32_t row = (uint32_t)(g / out_row_len), o = (uint32_t)(g % out_row_len);
+  Xyzz<T> acc = Xyzz<T>::inf();
+#pragma unroll 1
+  for (uint32_t i = 0; i < G; i++) {
+    uint32_t src = o * G + i;
+    if (src >= row_len) break;
+    Xyzz<T> q = load_xyzz<T>(in, (size_t)row * row_len + src);
+    xyzz_add_ni(acc, q);
+  }
+  store_xyzz(out, g, acc);
+}
+
+}  // namespace b200

@@ -1,0 +1,136 @@
+"""Host-side mirror of the reference's MSM interface on top of the C ABI.
+
+Names follow the reference:
+  multi_scalar_mul_vartime_parallel  <->  reference constantine/math/elliptic/ec_multi_scalar_mul_parallel.nim:588-628
+      (`tp.multiScalarMul_vartime_parallel(r, coefs, points, len)`, BigInt and Fr overloads), exported to C as
+      ctt_<curve>_<jac|prj>_multi_scalar_mul_<big|fr>_coefs_vartime_parallel (bindings/c_curve_decls_parallel.nim:31-45)
+  multi_scalar_mul_vartime           <->  reference constantine/math/elliptic/ec_multi_scalar_mul.nim:525-568 (serial twin)
+  Threadpool                          <->  reference constantine/threadpool/threadpool.nim:943-1041 (new / shutdown)
+
+Buffers are `bytes`/`bytearray`/numpy arrays/anything exposing the buffer protocol, laid out exactly like the
+reference's C structs (see include/ctt_b200_msm.h). Results come back as `bytes` of the _jac / _prj struct.
+Every call goes through the named extern "C" symbol -- this module adds no arithmetic.
+"""
+import ctypes
+
+from . import _lib
+from .curves import CURVES, CurveParams
+
+OUT_JAC, OUT_PRJ, OUT_XYZZ = 0, 1, 2
+
+
+def _curve(curve) -> CurveParams:
+    return curve if isinstance(curve, CurveParams) else CURVES[curve]
+
+
+def _buf(b):
+    """ctypes view of a read-only buffer without copying when possible."""
+    if isinstance(b, (bytes, bytearray)):
+        return (ctypes.c_char * len(b)).from_buffer_copy(b) if isinstance(b, bytes) else (ctypes.c_char * len(b)).from_buffer(b)
+    mv = memoryview(b).cast("B")
+    if mv.readonly:
+        return (ctypes.c_char * len(mv)).from_buffer_copy(mv)
+    return (ctypes.c_char * len(mv)).from_buffer(mv)
+
+
+class Threadpool:
+    """Opaque handle kept for source compatibility with reference callers (`Threadpool.new(n)` / `shutdown`)."""
+
+    def __init__(self, num_threads: int = 0):
+        lib = _lib.load()
+        self._h = lib.ctt_threadpool_new(num_threads or lib.ctt_cpu_get_num_threads_os())
+
+    @classmethod
+    def new(cls, num_threads: int = 0):
+        return cls(num_threads)
+
+    def shutdown(self):
+        if self._h:
+            _lib.load().ctt_threadpool_shutdown(self._h)
+            self._h = None
+
+
+def _symbol(curve: CurveParams, out: str, coef_kind: str, parallel: bool) -> str:
+    return f"ctt_{curve.cprefix}_{out}_multi_scalar_mul_{coef_kind}_coefs_vartime" + ("_parallel" if parallel else "")
+
+
+def multi_scalar_mul_vartime_parallel(tp, curve, coefs, points, length=None, out="jac", coef_kind="big") -> bytes:
+    """r <- [a0]P0 + ... + [a_{n-1}]P_{n-1}  through ctt_<curve>_<out>_multi_scalar_mul_<coef_kind>_coefs_vartime_parallel.
+
+    coefs: n x 32 bytes (canonical BigInt for coef_kind="big", Fr Montgomery residues for "fr");
+    points: n affine structs. Returns the _jac / _prj struct bytes.
+    """
+    cv = _curve(curve)
+    n = length if length is not None else len(memoryview(points).cast("B")) // cv.aff_bytes
+    fn = _lib.named_msm(_symbol(cv, out, coef_kind, True))
+    r = ctypes.create_string_buffer(cv.jac_bytes)
+    cb, pb = _buf(coefs), _buf(points)
+    fn(getattr(tp, "_h", None), r, cb, pb, n)
+    return r.raw
+
+
+def multi_scalar_mul_vartime(curve, coefs, points, length=None, out="jac", coef_kind="big") -> bytes:
+    cv = _curve(curve)
+    n = length if length is not None else len(memoryview(points).cast("B")) // cv.aff_bytes
+    fn = _lib.named_msm(_symbol(cv, out, coef_kind, False))
+    r = ctypes.create_string_buffer(cv.jac_bytes)
+    cb, pb = _buf(coefs), _buf(points)
+    fn(r, cb, pb, n)
+    return r.raw
+
+
+def msm_device_ptrs(curve, d_coefs: int, d_points: int, n: int, out=OUT_JAC, fr_mont=False, force_c=0,
+                    win_begin=0, win_end=-1) -> bytes:
+    """MSM over device-resident inputs (raw device pointers, e.g. torch tensor .data_ptr())."""
+    cv = _curve(curve)
+    size = cv.coord_bytes * (4 if out == OUT_XYZZ else 3)
+    r = ctypes.create_string_buffer(size)
+    rc = _lib.load().ctt_b200_msm_device(cv.curve_id, out, r, d_coefs, d_points, n, int(fr_mont), force_c, win_begin, win_end)
+    if rc != 0:
+        raise ValueError("ctt_b200_msm_device: bad curve id")
+    return r.raw
+
+
+def sum_partials(curve, partials: bytes, count: int, out=OUT_JAC) -> bytes:
+    cv = _curve(curve)
+    size = cv.coord_bytes * (4 if out == OUT_XYZZ else 3)
+    r = ctypes.create_string_buffer(size)
+    rc = _lib.load().ctt_b200_sum_partials(cv.curve_id, out, r, _buf(partials), count)
+    if rc != 0:
+        raise ValueError("ctt_b200_sum_partials: bad curve id")
+    return r.raw
+
+
+def plan(curve, n: int, force_c: int = 0):
+    cv = _curve(curve)
+    c, w = ctypes.c_int(0), ctypes.c_int(0)
+    _lib.load().ctt_b200_plan(cv.curve_id, n, force_c, ctypes.byref(c), ctypes.byref(w))
+    return c.value, w.value
+
+
+def last_stats() -> dict:
+    s = _lib.Stats()
+    _lib.load().ctt_b200_last_stats(ctypes.byref(s))
+    return {k: getattr(s, k) for k, _ in s._fields_}
+
+
+class CachedBases:
+    """Device-resident bases (reference constantine-rust/constantine-halo2-zal/src/lib.rs:58-95 caching hooks)."""
+
+    def __init__(self, curve, points, length=None):
+        self.curve = _curve(curve)
+        self.n = length if length is not None else len(memoryview(points).cast("B")) // self.curve.aff_bytes
+        self._h = _lib.load().ctt_b200_bases_upload(self.curve.curve_id, _buf(points), self.n)
+
+    def msm(self, coefs, length=None, out=OUT_JAC, coef_kind="big") -> bytes:
+        n = length if length is not None else len(memoryview(coefs).cast("B")) // 32
+        r = ctypes.create_string_buffer(self.curve.jac_bytes)
+        rc = _lib.load().ctt_b200_msm_cached_bases(self._h, out, r, _buf(coefs), n, int(coef_kind == "fr"))
+        if rc != 0:
+            raise ValueError("ctt_b200_msm_cached_bases failed (len exceeds the cached bases?)")
+        return r.raw
+
+    def free(self):
+        if self._h:
+            _lib.load().ctt_b200_bases_free(self._h)
+            self._h = None

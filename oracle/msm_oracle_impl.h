@@ -1,0 +1,422 @@
+/* ORACLE -- test infrastructure, NOT product code (only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may build, load or call this).
+ *
+ * CPU restatement of the reference's MSM hot path, instantiated by msm_oracle.c for
+ *   NL  = 4 | 6   64-bit limbs of the coordinate prime field (BN254/Pallas/Vesta | BLS12-381)
+ *   EXT = 1 | 2   coordinate field degree (G1 over Fp | G2 over Fp2 = Fp[i]/(i^2+1))
+ * Every function cites the reference file:line it follows.  Parity status: pinned against the reference's
+ * EIP-2537 MSM vectors, its Sage scalar-mul vectors and the exact big-int tier (tests/test_oracle_*.py).
+ */
+
+#define CAT_(a, b, c) a##_##b##_##c
+#define CAT(a, b, c) CAT_(a, b, c)
+#define FN(name) CAT(name, NL, EXT)
+
+typedef struct { uint64_t l[NL]; } FN(fp);
+typedef struct { FN(fp) c[EXT]; } FN(fe);                 /* coordinate-field element */
+typedef struct { FN(fe) x, y; } FN(aff);                  /* EC_ShortW_Aff, reference ec_shortweierstrass_affine.nim:32-37 */
+typedef struct { FN(fe) x, y, z; } FN(jac);               /* EC_ShortW_Jac, reference ec_shortweierstrass_jacobian.nim:28-38 */
+
+#define fp_t FN(fp)
+#define fe_t FN(fe)
+#define aff_t FN(aff)
+#define jac_t FN(jac)
+
+/* ------------------------------------------------------------------ prime field (Montgomery residues) */
+
+static inline int FN(fp_is_zero)(const fp_t* a) {
+  uint64_t o = 0;
+  for (int i = 0; i < NL; i++) o |= a->l[i];
+  return o == 0;
+}
+static inline int FN(fp_eq)(const fp_t* a, const fp_t* b) {
+  uint64_t o = 0;
+  for (int i = 0; i < NL; i++) o |= a->l[i] ^ b->l[i];
+  return o == 0;
+}
+static inline int FN(fp_geq_p)(const fp_t* a, const field_t* f) {
+  for (int i = NL - 1; i >= 0; i--) {
+    if (a->l[i] > f->p[i]) return 1;
+    if (a->l[i] < f->p[i]) return 0;
+  }
+  return 1;
+}
+static inline void FN(fp_sub_p)(fp_t* a, const field_t* f) {
+  u128 b = 0;
+  for (int i = 0; i < NL; i++) {
+    u128 d = (u128)a->l[i] - f->p[i] - b;
+    a->l[i] = (uint64_t)d;
+    b = (d >> 64) & 1;
+  }
+}
+/* reference finite_fields.nim:172-185 (sum): add then conditional subtract of the modulus */
+static inline void FN(fp_add)(fp_t* r, const fp_t* a, const fp_t* b, const field_t* f) {
+  u128 c = 0;
+  for (int i = 0; i < NL; i++) { c += (u128)a->l[i] + b->l[i]; r->l[i] = (uint64_t)c; c >>= 64; }
+  if (c || FN(fp_geq_p)(r, f)) FN(fp_sub_p)(r, f);
+}
+/* reference finite_fields.nim:199-210 (diff): subtract then conditional add of the modulus */
+static inline void FN(fp_sub)(fp_t* r, const fp_t* a, const fp_t* b, const field_t* f) {
+  u128 bw = 0;
+  for (int i = 0; i < NL; i++) {
+    u128 d = (u128)a->l[i] - b->l[i] - bw;
+    r->l[i] = (uint64_t)d;
+    bw = (d >> 64) & 1;
+  }
+  if (bw) {
+    u128 c = 0;
+    for (int i = 0; i < NL; i++) { c += (u128)r->l[i] + f->p[i]; r->l[i] = (uint64_t)c; c >>= 64; }
+  }
+}
+/* reference finite_fields.nim:340-358 (neg): p - a, with -0 = 0 */
+static inline void FN(fp_neg)(fp_t* r, const fp_t* a, const field_t* f) {
+  if (FN(fp_is_zero)(a)) { *r = *a; return; }
+  u128 bw = 0;
+  for (int i = 0; i < NL; i++) {
+    u128 d = (u128)f->p[i] - a->l[i] - bw;
+    r->l[i] = (uint64_t)d;
+    bw = (d >> 64) & 1;
+  }
+}
+/* reference finite_fields.nim:246-266 (div2): (a + (a odd ? p : 0)) >> 1 -- valid on Montgomery residues */
+static inline void FN(fp_div2)(fp_t* r, const fp_t* a, const field_t* f) {
+  uint64_t t[NL + 1];
+  u128 c = 0;
+  uint64_t odd = a->l[0] & 1;
+  for (int i = 0; i < NL; i++) { c += (u128)a->l[i] + (odd ? f->p[i] : 0); t[i] = (uint64_t)c; c >>= 64; }
+  t[NL] = (uint64_t)c;
+  for (int i = 0; i < NL; i++) r->l[i] = (t[i] >> 1) | (t[i + 1] << 63);
+}
+/* reference limbs_montgomery.nim:180-217 (mulMont_CIOS_sparebit): coarsely integrated operand scanning,
+ * one interleaved reduction per limb of b; final conditional subtraction (finite_fields.nim:268-281 keeps
+ * values canonical unless lazyReduce is requested -- the oracle never uses lazyReduce). */
+static inline void FN(fp_mul)(fp_t* r, const fp_t* a, const fp_t* b, const field_t* f) {
+  uint64_t t[NL + 2];
+  for (int i = 0; i < NL + 2; i++) t[i] = 0;
+  for (int i = 0; i < NL; i++) {
+    u128 c = 0;
+    for (int j = 0; j < NL; j++) {
+      c += (u128)a->l[j] * b->l[i] + t[j];
+      t[j] = (uint64_t)c; c >>= 64;
+    }
+    c += t[NL]; t[NL] = (uint64_t)c; t[NL + 1] = (uint64_t)(c >> 64);
+    uint64_t m = t[0] * f->m0ninv;
+    c = (u128)m * f->p[0] + t[0];
+    c >>= 64;
+    for (int j = 1; j < NL; j++) {
+      c += (u128)m * f->p[j] + t[j];
+      t[j - 1] = (uint64_t)c; c >>= 64;
+    }
+    c += t[NL]; t[NL - 1] = (uint64_t)c; c >>= 64;
+    t[NL] = t[NL + 1] + (uint64_t)c;
+  }
+  fp_t o;
+  for (int i = 0; i < NL; i++) o.l[i] = t[i];
+  if (t[NL] || FN(fp_geq_p)(&o, f)) FN(fp_sub_p)(&o, f);
+  *r = o;
+}
+
+/* ------------------------------------------------------------------ coordinate field: Fp or Fp2 */
+static inline int FN(fe_is_zero)(const fe_t* a) {
+  for (int k = 0; k < EXT; k++) if (!FN(fp_is_zero)(&a->c[k])) return 0;
+  return 1;
+}
+static inline int FN(fe_eq)(const fe_t* a, const fe_t* b) {
+  for (int k = 0; k < EXT; k++) if (!FN(fp_eq)(&a->c[k], &b->c[k])) return 0;
+  return 1;
+}
+static inline void FN(fe_add)(fe_t* r, const fe_t* a, const fe_t* b, const field_t* f) {
+  for (int k = 0; k < EXT; k++) FN(fp_add)(&r->c[k], &a->c[k], &b->c[k], f);
+}
+static inline void FN(fe_sub)(fe_t* r, const fe_t* a, const fe_t* b, const field_t* f) {
+  for (int k = 0; k < EXT; k++) FN(fp_sub)(&r->c[k], &a->c[k], &b->c[k], f);
+}
+static inline void FN(fe_neg)(fe_t* r, const fe_t* a, const field_t* f) {
+  for (int k = 0; k < EXT; k++) FN(fp_neg)(&r->c[k], &a->c[k], f);
+}
+static inline void FN(fe_div2)(fe_t* r, const fe_t* a, const field_t* f) {
+  for (int k = 0; k < EXT; k++) FN(fp_div2)(&r->c[k], &a->c[k], f);
+}
+static inline void FN(fe_mul)(fe_t* r, const fe_t* a, const fe_t* b, const field_t* f) {
+#if EXT == 1
+  FN(fp_mul)(&r->c[0], &a->c[0], &b->c[0], f);
+#else
+  /* reference extension_fields/towers.nim:798-885 (complex multiplication, i^2 = -1, Karatsuba) */
+  fp_t v0, v1, s0, s1, t;
+  FN(fp_mul)(&v0, &a->c[0], &b->c[0], f);
+  FN(fp_mul)(&v1, &a->c[1], &b->c[1], f);
+  FN(fp_add)(&s0, &a->c[0], &a->c[1], f);
+  FN(fp_add)(&s1, &b->c[0], &b->c[1], f);
+  FN(fp_mul)(&t, &s0, &s1, f);
+  FN(fp_sub)(&t, &t, &v0, f);
+  FN(fp_sub)(&r->c[1], &t, &v1, f);
+  FN(fp_sub)(&r->c[0], &v0, &v1, f);
+#endif
+}
+static inline void FN(fe_sqr)(fe_t* r, const fe_t* a, const field_t* f) {
+#if EXT == 1
+  FN(fp_mul)(&r->c[0], &a->c[0], &a->c[0], f);
+#else
+  /* reference extension_fields/towers.nim:798-885 (complex squaring): (a0+a1)(a0-a1) + 2 a0 a1 i */
+  fp_t s, d, t;
+  FN(fp_add)(&s, &a->c[0], &a->c[1], f);
+  FN(fp_sub)(&d, &a->c[0], &a->c[1], f);
+  FN(fp_mul)(&t, &a->c[0], &a->c[1], f);
+  FN(fp_mul)(&r->c[0], &s, &d, f);
+  FN(fp_add)(&r->c[1], &t, &t, f);
+#endif
+}
+static inline void FN(fe_set_one)(fe_t* r, const field_t* f) {
+  memset(r, 0, sizeof(*r));
+  for (int i = 0; i < NL; i++) r->c[0].l[i] = f->one[i];
+}
+static inline int FN(fe_is_one)(const fe_t* a, const field_t* f) {
+  for (int i = 0; i < NL; i++) if (a->c[0].l[i] != f->one[i]) return 0;
+  for (int k = 1; k < EXT; k++) if (!FN(fp_is_zero)(&a->c[k])) return 0;
+  return 1;
+}
+
+/* ------------------------------------------------------------------ points */
+/* reference ec_shortweierstrass_affine.nim:52-62: affine infinity is (0, 0) */
+static inline int FN(aff_is_inf)(const aff_t* p) { return FN(fe_is_zero)(&p->x) && FN(fe_is_zero)(&p->y); }
+/* reference ec_shortweierstrass_jacobian.nim:46-63: neutral iff Z == 0, written as (1, 1, 0) */
+static inline int FN(jac_is_inf)(const jac_t* p) { return FN(fe_is_zero)(&p->z); }
+static inline void FN(jac_set_inf)(jac_t* p, const field_t* f) {
+  FN(fe_set_one)(&p->x, f); FN(fe_set_one)(&p->y, f); memset(&p->z, 0, sizeof(p->z));
+}
+/* reference ec_shortweierstrass_jacobian.nim:666-673 (fromAffine) */
+static inline void FN(jac_from_aff)(jac_t* r, const aff_t* q, const field_t* f) {
+  if (FN(aff_is_inf)(q)) { FN(jac_set_inf)(r, f); return; }
+  r->x = q->x; r->y = q->y; FN(fe_set_one)(&r->z, f);
+}
+
+/* reference ec_shortweierstrass_jacobian.nim:564-592 (dbl_1998_cmo_rescaled_a0_impl):
+ *   YY = Y^2, M = 3X^2/2, S = X*YY, X3 = M^2 - 2S, Y3 = M(S - X3) - YY^2, Z3 = Y*Z */
+static void FN(jac_dbl)(jac_t* r, const jac_t* p, const field_t* f) {
+  fe_t Y, M, S, t;
+  jac_t o;
+  FN(fe_sqr)(&Y, &p->y, f);
+  FN(fe_sqr)(&M, &p->x, f);
+  FN(fe_add)(&t, &M, &M, f); FN(fe_add)(&M, &t, &M, f);
+  FN(fe_div2)(&M, &M, f);
+  FN(fe_mul)(&S, &p->x, &Y, f);
+  FN(fe_sqr)(&Y, &Y, f);
+  FN(fe_mul)(&o.z, &p->z, &p->y, f);
+  FN(fe_sqr)(&o.x, &M, f);
+  FN(fe_sub)(&o.x, &o.x, &S, f);
+  FN(fe_sub)(&o.x, &o.x, &S, f);
+  FN(fe_sub)(&o.y, &S, &o.x, f);
+  FN(fe_mul)(&o.y, &o.y, &M, f);
+  FN(fe_sub)(&o.y, &o.y, &Y, f);
+  *r = o;
+}
+
+/* shared tail of sum_vartime / mixedSum_vartime once U1, S1, H, R are known
+ * (reference ec_shortweierstrass_jacobian.nim:760-796 and :866-896) */
+static inline void FN(jac_add_tail)(jac_t* r, fe_t* U, const fe_t* S, const fe_t* H, const fe_t* R, const field_t* f) {
+  fe_t HHH, t;
+  FN(fe_sqr)(&HHH, H, f);
+  FN(fe_mul)(U, U, &HHH, f);          /* V = U1*HH */
+  FN(fe_mul)(&HHH, &HHH, H, f);       /* HHH */
+  FN(fe_sqr)(&t, R, f);
+  FN(fe_sub)(&t, &t, U, f);
+  FN(fe_sub)(&t, &t, U, f);
+  FN(fe_sub)(&r->x, &t, &HHH, f);     /* X3 = R^2 - HHH - 2V */
+  FN(fe_sub)(U, U, &r->x, f);
+  FN(fe_mul)(U, U, R, f);
+  FN(fe_mul)(&HHH, &HHH, S, f);
+  FN(fe_sub)(&r->y, U, &HHH, f);      /* Y3 = R(V - X3) - S1*HHH */
+}
+
+/* reference ec_shortweierstrass_jacobian.nim:681-796 (sum_vartime), Cohen-Miyaji-Ono 1998 */
+static void FN(jac_add)(jac_t* r, const jac_t* p, const jac_t* q, const field_t* f) {
+  if (FN(jac_is_inf)(p)) { *r = *q; return; }
+  if (FN(jac_is_inf)(q)) { *r = *p; return; }
+  int isPz1 = FN(fe_is_one)(&p->z, f), isQz1 = FN(fe_is_one)(&q->z, f);
+  fe_t U, S, H, R;
+  jac_t o;
+  if (!isPz1) FN(fe_sqr)(&R, &p->z, f);                  /* Z1Z1 */
+  if (isQz1) {
+    U = p->x;
+    if (isPz1) H = q->x; else FN(fe_mul)(&H, &q->x, &R, f);
+    FN(fe_sub)(&H, &H, &U, f);
+    S = p->y;
+  } else {
+    FN(fe_sqr)(&S, &q->z, f);                            /* Z2Z2 */
+    FN(fe_mul)(&U, &p->x, &S, f);
+    if (isPz1) H = q->x; else FN(fe_mul)(&H, &q->x, &R, f);
+    FN(fe_sub)(&H, &H, &U, f);
+    FN(fe_mul)(&S, &S, &q->z, f);
+    FN(fe_mul)(&S, &S, &p->y, f);
+  }
+  if (isPz1) R = q->y;
+  else { FN(fe_mul)(&R, &R, &p->z, f); FN(fe_mul)(&R, &R, &q->y, f); }
+  FN(fe_sub)(&R, &R, &S, f);
+  if (FN(fe_is_zero)(&H)) {
+    if (FN(fe_is_zero)(&R)) { FN(jac_dbl)(r, p, f); return; }
+    FN(jac_set_inf)(r, f); return;
+  }
+  /* Z3 = Z1*Z2*H */
+  if (isPz1) { if (isQz1) o.z = H; else FN(fe_mul)(&o.z, &H, &q->z, f); }
+  else { if (isQz1) FN(fe_mul)(&o.z, &H, &p->z, f); else { FN(fe_mul)(&o.z, &p->z, &q->z, f); FN(fe_mul)(&o.z, &o.z, &H, f); } }
+  FN(jac_add_tail)(&o, &U, &S, &H, &R, f);
+  *r = o;
+}
+
+/* reference ec_shortweierstrass_jacobian.nim:798-896 (mixedSum_vartime) */
+static void FN(jac_madd)(jac_t* r, const jac_t* p, const aff_t* q, const field_t* f) {
+  if (FN(jac_is_inf)(p)) { FN(jac_from_aff)(r, q, f); return; }
+  if (FN(aff_is_inf)(q)) { *r = *p; return; }
+  int isPz1 = FN(fe_is_one)(&p->z, f);
+  fe_t U, S, H, R;
+  jac_t o;
+  if (!isPz1) FN(fe_sqr)(&R, &p->z, f);
+  U = p->x;
+  if (isPz1) H = q->x; else FN(fe_mul)(&H, &q->x, &R, f);
+  FN(fe_sub)(&H, &H, &U, f);
+  S = p->y;
+  if (isPz1) R = q->y;
+  else { FN(fe_mul)(&R, &R, &p->z, f); FN(fe_mul)(&R, &R, &q->y, f); }
+  FN(fe_sub)(&R, &R, &S, f);
+  if (FN(fe_is_zero)(&H)) {
+    if (FN(fe_is_zero)(&R)) { FN(jac_dbl)(r, p, f); return; }
+    FN(jac_set_inf)(r, f); return;
+  }
+  if (isPz1) o.z = H; else FN(fe_mul)(&o.z, &H, &p->z, f);
+  FN(jac_add_tail)(&o, &U, &S, &H, &R, f);
+  *r = o;
+}
+
+/* buckets[val-1] +/-= point   (reference ec_multi_scalar_mul.nim:177-184, accumulate) */
+static inline void FN(accumulate)(jac_t* buckets, uint64_t val, int neg, const aff_t* pt, const field_t* f) {
+  if (val == 0) return;
+  if (neg) {
+    aff_t n = *pt;
+    FN(fe_neg)(&n.y, &pt->y, f);
+    FN(jac_madd)(&buckets[val - 1], &buckets[val - 1], &n, f);
+  } else {
+    FN(jac_madd)(&buckets[val - 1], &buckets[val - 1], pt, f);
+  }
+}
+
+/* running-sum bucket reduction  (reference ec_multi_scalar_mul.nim:186-197, bucketReduce) */
+static void FN(bucket_reduce)(jac_t* r, jac_t* buckets, size_t num_buckets, const field_t* f) {
+  jac_t accum = buckets[num_buckets - 1];
+  *r = buckets[num_buckets - 1];
+  for (size_t k = num_buckets - 1; k-- > 0;) {
+    FN(jac_add)(&accum, &accum, &buckets[k], f);
+    FN(jac_add)(r, r, &accum, f);
+  }
+}
+
+/* One window: init buckets, accumulate all N points with signed digits, reduce.
+ * reference ec_multi_scalar_mul_parallel.nim:137-146 (bucketAccumReduce_withInit) +
+ *           ec_multi_scalar_mul.nim:204-235 (bucketAccumReduce).
+ * kind: 0 bottom, 1 full, 2 top (reference MiniMsmKind, ec_multi_scalar_mul.nim:199-202) */
+static void FN(window_signed)(jac_t* window_sum, int kind, int bit_index, int c, int bits,
+                              const uint64_t* coefs, const aff_t* points, size_t n, const field_t* f) {
+  size_t nb = (size_t)1 << (c - 1);
+  jac_t* buckets = (jac_t*)malloc(nb * sizeof(jac_t));
+  for (size_t i = 0; i < nb; i++) FN(jac_set_inf)(&buckets[i], f);
+  int excess = bits % c, top = bits - excess;
+  for (size_t j = 0; j < n; j++) {
+    uint64_t val; int neg;
+    const uint64_t* k = coefs + j * SCALAR_LIMBS;
+    if (kind == 0) signed_bottom_window(k, c, &val, &neg);
+    else if (kind == 2) signed_top_window(k, top, excess, &val, &neg);
+    else signed_full_window(k, bit_index, c, &val, &neg);
+    FN(accumulate)(buckets, val, neg, &points[j], f);
+  }
+  FN(bucket_reduce)(window_sum, buckets, nb, f);
+  free(buckets);
+}
+
+typedef struct {
+  jac_t* out; int kind, bit_index, c, bits; const uint64_t* coefs; const aff_t* points; size_t n; const field_t* f;
+} FN(wtask);
+
+static void FN(run_wtask)(void* arg) {
+  FN(wtask)* t = (FN(wtask)*)arg;
+  FN(window_signed)(t->out, t->kind, t->bit_index, t->c, t->bits, t->coefs, t->points, t->n, t->f);
+}
+
+/* Signed-window bucket MSM with one task per window -- the structure of
+ * reference ec_multi_scalar_mul_parallel.nim:148-208 (msmImpl_vartime_parallel):
+ *   numFullWindows = bits div c, numWindows = numFullWindows + 1 (the recoding needs to see an extra 0 after
+ *   the MSB even when c divides bits), top window kind per :186-190, Horner with c doublings per window :198-203.
+ * For c >= 9 the reference swaps Jacobian buckets for the batched-affine scheduler (:316-431) -- a CPU cache
+ * optimisation that yields the same group element and is not restated. */
+static void FN(msm_signed)(jac_t* r, const uint64_t* coefs, const aff_t* points, size_t n, int c, int bits,
+                           const field_t* f, int nthreads) {
+  int num_full = bits / c;
+  int excess = bits % c, top = bits - excess;
+  jac_t* sums = (jac_t*)malloc((size_t)(num_full + 1) * sizeof(jac_t));
+  FN(wtask)* tasks = (FN(wtask)*)malloc((size_t)(num_full + 1) * sizeof(FN(wtask)));
+  for (int w = 0; w <= num_full; w++) {
+    int kind = (w == 0) ? 0 : 1;
+    int bit_index = w * c;
+    if (w == num_full) { kind = (top == 0) ? 0 : (excess == 0 ? 1 : 2); bit_index = top; }
+    FN(wtask) t = { &sums[w], kind, bit_index, c, bits, coefs, points, n, f };
+    tasks[w] = t;
+  }
+  run_tasks(FN(run_wtask), tasks, sizeof(FN(wtask)), num_full + 1, nthreads);
+  *r = sums[num_full];
+  for (int w = num_full - 1; w >= 0; w--) {
+    for (int i = 0; i < c; i++) FN(jac_dbl)(r, r, f);
+    FN(jac_add)(r, r, &sums[w], f);
+  }
+  free(tasks);
+  free(sums);
+}
+
+/* Unsigned-window textbook bucket method
+ * (reference ec_multi_scalar_mul.nim:40-95, multiScalarMulImpl_reference_vartime, "BDLO12 section 4") */
+static void FN(msm_reference)(jac_t* r, const uint64_t* coefs, const aff_t* points, size_t n, int c, int bits,
+                              const field_t* f) {
+  size_t nb = ((size_t)1 << c) - 1;
+  int num_windows = (bits + c - 1) / c;
+  jac_t* buckets = (jac_t*)malloc(nb * sizeof(jac_t));
+  jac_t* mini = (jac_t*)malloc((size_t)num_windows * sizeof(jac_t));
+  for (int w = 0; w < num_windows; w++) {
+    for (size_t i = 0; i < nb; i++) FN(jac_set_inf)(&buckets[i], f);
+    for (size_t j = 0; j < n; j++) {
+      uint64_t b = get_window_at(coefs + j * SCALAR_LIMBS, w * c, c);
+      if (b == 0) continue;
+      FN(jac_madd)(&buckets[b - 1], &buckets[b - 1], &points[j], f);
+    }
+    jac_t accum = buckets[nb - 1];
+    jac_t m = buckets[nb - 1];
+    for (size_t k = nb - 1; k-- > 0;) {
+      FN(jac_add)(&accum, &accum, &buckets[k], f);
+      FN(jac_add)(&m, &m, &accum, f);
+    }
+    mini[w] = m;
+  }
+  *r = mini[num_windows - 1];
+  for (int w = num_windows - 2; w >= 0; w--) {
+    for (int i = 0; i < c; i++) FN(jac_dbl)(r, r, f);
+    FN(jac_add)(r, r, &mini[w], f);
+  }
+  free(buckets);
+  free(mini);
+}
+
+/* naive sum of double-and-add scalar multiplications
+ * (the "naive" side of reference tests/math_elliptic_curves/t_ec_template.nim:1466-1480) */
+static void FN(msm_naive)(jac_t* r, const uint64_t* coefs, const aff_t* points, size_t n, int bits, const field_t* f) {
+  FN(jac_set_inf)(r, f);
+  for (size_t j = 0; j < n; j++) {
+    jac_t acc; FN(jac_set_inf)(&acc, f);
+    const uint64_t* k = coefs + j * SCALAR_LIMBS;
+    for (int b = bits - 1; b >= 0; b--) {
+      FN(jac_dbl)(&acc, &acc, f);
+      if ((k[b >> 6] >> (b & 63)) & 1) FN(jac_madd)(&acc, &acc, &points[j], f);
+    }
+    FN(jac_add)(r, r, &acc, f);
+  }
+}
+
+#undef fp_t
+#undef fe_t
+#undef aff_t
+#undef jac_t
