@@ -1,0 +1,370 @@
+#!/usr/bin/env python3
+"""bench.py -- BLS12-381 G1 multi-scalar-multiplication throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--logn 20]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one MSM of 2^logn (scalar, point) pairs (configs[2]: BLS12-381 G1, N = 2^20, uniform 255-bit scalars not
+reduced mod r, points in the prime-order subgroup).  Prints ONE JSON line on rank 0.
+
+  value   MSMs/s, inputs resident in HBM when the timed region starts (ctt_b200_msm_device), CUDA events on the stream
+          the kernels are launched on, max over ranks.  N > 1: ONE MSM per step sharded over the ranks by points
+          (strong scaling) + all_gather of the <= N partial points (NCCL) + host combine, inside the timed region.
+  e2e     same metric through the reference's own C symbol ctt_bls12_381_g1_jac_multi_scalar_mul_big_coefs_vartime_parallel
+          with HOST (pinned) buffers: H2D of scalars+points and D2H of the window sums inside the timed region.
+  roofline  dominant kernel k_accumulate: algorithmic 32x32->64 integer MACs (3300 per bucket point-add)
+          / its CUDA-event duration, against the measured IMAD.WIDE issue peak (profiles/ubench_r1.jsonl); the HBM
+          fraction (algorithmic bytes / step time vs MEASURED_PEAKS.json) is reported beside it.
+  cpu_baseline  the oracle's restatement of the reference's CPU algorithm (kind "port": the Nim reference cannot be
+          built in this image) on all host cores, bounded sample.
+--impl reference times that same CPU restatement as the reference arm.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CURVE = "bls12_381_g1"
+INT_MACS_PER_POINT_ADD = 3300            # 11 field mults x (2*12^2 + 12) MACs, BLS12-381 G1
+ALGO_BYTES_PER_TERM = 128                # 32 B scalar + 96 B affine point
+# Measured on this pool's B200 (tools/ubench.cu, profiles/ubench_r1.jsonl): mad.wide.u32 issues at 63.7 /clk/SM
+# => 148 SMs x 63.7 x 1.965 GHz = 18.5e12 32x32->64 MACs/s.  (IMAD.WIDE with carry-in/out runs at half that.)
+INT_MAC_PEAK_PER_S = 18.52e12
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.reasons = set()
+        self._stop = threading.Event()
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def make_inputs(n, seed):
+    """Synthetic inputs: scalars uniform in [0, 2^255) (not reduced mod r, like reference
+    benchmarks/bench_elliptic_parallel_template.nim:90); points P_i = [k_i]G with random 64-bit k_i, computed on the GPU
+    by the library's generator hook (prime-order subgroup by construction). Returns numpy uint8 arrays + the k_i."""
+    import numpy as np
+    from constantine_b200 import _lib
+    from constantine_b200.curves import CURVES
+    cv = CURVES[CURVE]
+    rng = np.random.default_rng(seed)
+    scal = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    scal[:, 31] &= 0x7F
+    k = rng.integers(1, 2**63, size=n, dtype=np.uint64)
+    gen = np.frombuffer(_gen_bytes(cv), dtype=np.uint8).copy()
+    pts = np.empty((n, cv.aff_bytes), dtype=np.uint8)
+    lib = _lib.load()
+    rc = lib.ctt_b200_scalar_mul_u64(cv.curve_id, gen.ctypes.data, k.ctypes.data, n, pts.ctypes.data)
+    assert rc == 0
+    return scal, pts, k
+
+
+def _gen_bytes(cv):
+    f = cv.fp
+    out = b""
+    for coord in cv.gen:
+        for c in coord:
+            out += f.to_mont(c).to_bytes(f.nbytes, "little")
+    return out
+
+
+def algorithmic_point_adds(n, c, bits=255):
+    """W*(N + 2*2^(c-1)) + W*(c+1), W = floor(b/c)+1."""
+    W = bits // c + 1
+    return W * (n + 2 * (1 << (c - 1))) + W * (c + 1)
+
+
+def time_oracle(n_full, budget_s=20.0, max_logn=20):
+    """CPU baseline: the oracle's signed-window one-task-per-window MSM (restatement of the reference's
+    msmImpl_vartime_parallel with the reference's own window choice) on all host cores, on a bounded sample."""
+    import numpy as np
+    from constantine_b200.curves import CURVES
+    from oracle import oracle
+    cv = CURVES[CURVE]
+    cores = os.cpu_count() or 1
+    oracle.build()
+    lib = oracle.load()
+    cvt = oracle.curve_t(cv)
+    # points for the CPU sample: multiples of G generated by the oracle itself is not needed -- timing does not depend on
+    # the values, so reuse a small pool of valid points produced by the exact tier.
+    from oracle import pyref
+    import random
+    rnd = random.Random(99)
+    pool = np.frombuffer(b"".join(pyref.aff_to_bytes(pyref.ec_mul_fast(rnd.getrandbits(64) | 1, cv.gen, cv), cv) for _ in range(256)),
+                         dtype=np.uint8).reshape(256, cv.aff_bytes)
+    rng = np.random.default_rng(5)
+
+    def run(logn):
+        n = 1 << logn
+        pts = pool[rng.integers(0, 256, size=n)]
+        scal = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        scal[:, 31] &= 0x7F
+        out = ctypes.create_string_buffer(cv.jac_bytes)
+        pts = np.ascontiguousarray(pts)
+        t0 = time.perf_counter()
+        c = lib.oracle_msm(ctypes.byref(cvt), out, scal.ctypes.data, pts.ctypes.data, n, 0, oracle.IMPL_SIGNED, 0, cores)
+        return time.perf_counter() - t0, c
+
+    t14, _ = run(14)
+    logn = 14
+    while logn < max_logn and (1 << logn) < n_full and t14 * (1 << (logn + 1 - 14)) * 0.8 < budget_s:
+        logn += 1
+    t, c = run(logn) if logn > 14 else (t14, lib.oracle_parallel_dispatch_c(1 << 14, 255))
+    n = 1 << logn
+    padds = algorithmic_point_adds(n, c)
+    scale = n_full / n   # MSM cost is ~linear in N at these sizes (window count shrinks slowly): scaled, stated in `sample`
+    return {"value": 1.0 / (t * scale), "unit": "MSM/s", "cores": cores, "kind": "port",
+            "sample": f"one MSM of 2^{logn} pairs in {t:.2f} s (c={c}, {padds / t / 1e6:.1f} Mop point-adds/s), "
+                      f"scaled x{scale:g} to N=2^{n_full.bit_length() - 1}",
+            "point_adds_per_s": padds / t, "seconds": t, "logn": logn}
+
+
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    n = 1 << args.logn
+    vals = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        info = time_oracle(n, budget_s=12.0)
+        if i >= args.warmup:
+            vals.append(info["seconds"] * (n / (1 << info["logn"])))
+    ms = 1e3 * sum(vals) / len(vals)
+    v = 1e3 / ms
+    line = {"impl": "reference", "metric": "bls12_381_g1_msm_throughput", "value": v, "unit": "MSM/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"BLS12-381 G1 MSM N=2^{args.logn}, uniform 255-bit scalars", "note":
+                       "CPU restatement (oracle port) of the reference's parallel MSM on all host cores; the Nim reference "
+                       "itself cannot be built in this image"},
+            "cpu_baseline": {"value": v, "unit": "MSM/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]},
+            "e2e": {"value": v, "unit": "MSM/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--logn", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    from constantine_b200 import _lib, msm as M, sharded
+    from constantine_b200.curves import CURVES
+
+    rank, world, local = dist_env()
+    cv = CURVES[CURVE]
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    n = 1 << args.logn
+    lo, hi = sharded.balanced_chunk(n, world, rank)
+    n_loc = hi - lo
+    # every rank generates only its shard (same global seed => same global instance whatever the world size)
+    scal_all_seed = 0xC770003
+    scal, pts, _ = make_inputs(n, scal_all_seed) if world == 1 else make_inputs_shard(n, scal_all_seed, lo, hi)
+    h_scal = torch.from_numpy(scal).pin_memory()
+    h_pts = torch.from_numpy(pts).pin_memory()
+    d_scal = h_scal.to(dev)
+    d_pts = h_pts.to(dev)
+    torch.cuda.synchronize()
+    # run the engine on a torch-owned (non-default) stream so that torch.cuda.Event brackets exactly the launches
+    bench_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(bench_stream)
+    lib.ctt_b200_set_stream(ctypes.c_void_p(bench_stream.cuda_stream))
+
+    def step_resident():
+        if world == 1:
+            return M.msm_device_ptrs(cv, d_scal.data_ptr(), d_pts.data_ptr(), n_loc, out=M.OUT_JAC)
+        part = M.msm_device_ptrs(cv, d_scal.data_ptr(), d_pts.data_ptr(), n_loc, out=M.OUT_XYZZ)
+        return sharded.msm_point_sharded(cv, part, device=dev)
+
+    named = _lib.named_msm("ctt_bls12_381_g1_jac_multi_scalar_mul_big_coefs_vartime_parallel")
+    named_xyzz = lib.ctt_b200_msm_host
+    tp = M.Threadpool.new(1)
+    r_buf = ctypes.create_string_buffer(4 * cv.coord_bytes)
+
+    def step_e2e():
+        if world == 1:
+            named(tp._h, r_buf, h_scal.data_ptr(), h_pts.data_ptr(), n_loc)
+            return r_buf.raw[:cv.jac_bytes]
+        named_xyzz(cv.curve_id, M.OUT_XYZZ, r_buf, h_scal.data_ptr(), h_pts.data_ptr(), n_loc, 0)
+        return sharded.msm_point_sharded(cv, r_buf.raw, device=dev)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, collect=None):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+            if collect is not None:
+                collect(M.last_stats())
+        e1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ev_ms = e0.elapsed_time(e1)
+        ms = max(ev_ms, 0.0)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms, wall_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall_ms = t[0].item(), t[1].item()
+        return ms / steps, wall_ms / steps
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    stats = []
+    ms_res, wall_res = timed(step_resident, args.steps, args.warmup, collect=stats.append)
+    ms_e2e, wall_e2e = timed(step_e2e, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+
+    # correctness of what was timed: closed form is in tests; here cross-check the two paths against each other
+    ra, rb = step_resident(), step_e2e()
+    from oracle import pyref
+    same = pyref.jac_bytes_to_affine(ra, cv) == pyref.jac_bytes_to_affine(rb, cv)
+
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    st = stats[-1]
+    acc_ms = sum(s["ms_accumulate"] for s in stats) / len(stats)
+    madds = st["entries"]      # bucket point-adds issued by k_accumulate per launch (one per sorted entry, minus run heads)
+    macs = madds * INT_MACS_PER_POINT_ADD
+    achieved = macs / (acc_ms * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    algo_bytes = n_loc * ALGO_BYTES_PER_TERM
+    hbm_achieved = algo_bytes / (ms_res * 1e-3) / 1e9
+    padds = algorithmic_point_adds(n, st["c"])
+    line = {
+        "metric": "bls12_381_g1_msm_throughput", "value": 1e3 / ms_res, "unit": "MSM/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": f"BLS12-381 G1 MSM N=2^{args.logn} (BASELINE configs[2]), uniform 255-bit scalars, subgroup points",
+                   "parallelism": "1 GPU" if world == 1 else f"point-sharded over {world} GPUs + all_gather of partial points",
+                   "window_c": st["c"], "windows": st["num_windows"],
+                   "l2": "no flush needed: inputs (128 MiB) + sort/bucket scratch (~470 MiB) exceed the 126 MB L2"},
+        "point_adds_per_s": padds / (ms_res * 1e-3), "Mop_point_adds_per_s": padds / (ms_res * 1e-3) / 1e6,
+        "wall_ms_per_step": wall_res,
+        "e2e": {"value": 1e3 / ms_e2e, "unit": "MSM/s", "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e,
+                "h2d_bytes_per_step": int(n_loc * ALGO_BYTES_PER_TERM), "d2h_bytes_per_step": int(st["num_windows"] * 4 * cv.coord_bytes),
+                "api": "ctt_bls12_381_g1_jac_multi_scalar_mul_big_coefs_vartime_parallel (pinned host buffers)"},
+        "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
+        "phases_ms": {k: round(sum(s[k] for s in stats) / len(stats), 4) for k in
+                      ("ms_digits", "ms_sort", "ms_accumulate", "ms_fixup", "ms_reduce", "ms_d2h_tail", "ms_total")},
+        "roofline": {"bound": "int32-mad (neither hbm nor tensor: see roofline_hbm)", "kernel": "k_accumulate",
+                     "achieved": achieved / 1e12, "peak": INT_MAC_PEAK_PER_S / 1e12, "unit": "TMAC/s (32x32->64)",
+                     "frac": achieved / INT_MAC_PEAK_PER_S, "traffic": None,
+                     "peak_source": "measured IMAD.WIDE issue rate, tools/ubench.cu -> profiles/ubench_r1.jsonl",
+                     "algorithmic_work": f"{madds} bucket point-adds x {INT_MACS_PER_POINT_ADD} MACs per launch, {acc_ms:.3f} ms"},
+        "roofline_hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                         "traffic": None, "peak_source": hbm_src, "algorithmic_bytes": algo_bytes},
+        "clocks": clocks, "paths_agree": bool(same),
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = {k: v for k, v in time_oracle(n).items() if k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def make_inputs_shard(n, seed, lo, hi):
+    """Rank-local shard of the global instance: the global scalar / multiplier streams are generated with the same seed on
+    every rank and sliced, so the instance does not depend on the world size."""
+    import numpy as np
+    from constantine_b200 import _lib
+    from constantine_b200.curves import CURVES
+    cv = CURVES[CURVE]
+    rng = np.random.default_rng(seed)
+    scal = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    scal[:, 31] &= 0x7F
+    k = rng.integers(1, 2**63, size=n, dtype=np.uint64)
+    scal, k = np.ascontiguousarray(scal[lo:hi]), np.ascontiguousarray(k[lo:hi])
+    gen = np.frombuffer(_gen_bytes(cv), dtype=np.uint8).copy()
+    pts = np.empty((hi - lo, cv.aff_bytes), dtype=np.uint8)
+    rc = _lib.load().ctt_b200_scalar_mul_u64(cv.curve_id, gen.ctypes.data, k.ctypes.data, hi - lo, pts.ctypes.data)
+    assert rc == 0
+    return scal, pts, k
+
+
+if __name__ == "__main__":
+    main()

@@ -49,6 +49,8 @@ def load():
     lib.ctt_b200_last_stats.restype = None
     lib.ctt_b200_set_tuning.argtypes = [ci, ci, ci]
     lib.ctt_b200_set_tuning.restype = None
+    lib.ctt_b200_set_stream.argtypes = [vp]
+    lib.ctt_b200_set_stream.restype = None
     lib.ctt_b200_sm_count.argtypes = []
     lib.ctt_b200_sm_count.restype = ci
     lib.ctt_b200_test_field_op.argtypes = [ci, ci, vp, vp, vp, sz]

@@ -116,8 +116,8 @@ int ctt_b200_msm_cached_bases(const ctt_b200_bases* bases, int out_kind, void* r
     std::lock_guard<std::mutex> lock(E.mu);
     E.init();
     E.d_scalars.ensure(len * 32 + 16);
-    B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, len * 32, cudaMemcpyHostToDevice, E.stream));
-    B200_CUDA_CHECK(cudaStreamSynchronize(E.stream));
+    B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, len * 32, cudaMemcpyHostToDevice, E.compute()));
+    B200_CUDA_CHECK(cudaStreamSynchronize(E.compute()));
   }
   return ctt_b200_msm_device(b->curve_id, out_kind, r, E.d_scalars.ptr, b->d_points, len, fr_mont, 0, 0, -1);
 }
@@ -136,6 +136,12 @@ void ctt_b200_set_tuning(int force_c, int reduce_chunk, int sum_group) {
   if (force_c < 0) E.tuning.force_c = 0;
   if (reduce_chunk > 0) E.tuning.reduce_chunk = reduce_chunk;
   if (sum_group > 0) E.tuning.sum_group = sum_group;
+}
+
+void ctt_b200_set_stream(void* cuda_stream) {
+  Engine& E = engine();
+  std::lock_guard<std::mutex> lock(E.mu);
+  E.user_stream = (cudaStream_t)cuda_stream;
 }
 
 int ctt_b200_sm_count(void) {

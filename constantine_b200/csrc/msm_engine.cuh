@@ -118,6 +118,8 @@ struct Engine {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t user_stream = nullptr;  // optional caller-provided compute stream (ctt_b200_set_stream)
+  cudaStream_t compute() const { return user_stream ? user_stream : stream; }
   cudaEvent_t ev[10];
   cudaEvent_t ev_points_ready;
   DeviceBuffer d_scalars, d_points, keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_pts[2], part_keys[2], red_a, red_b;
@@ -185,7 +187,7 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   constexpr size_t XYZZ_BYTES = 4 * T::WORDS * 4;
   st.c = c; st.num_windows = nw; st.entries = entries; st.total_buckets = nbuckets;
 
-  cudaStream_t s = E.stream;
+  cudaStream_t s = E.compute();
   E.keys_a.ensure(entries * 4); E.keys_b.ensure(entries * 4);
   E.vals_a.ensure(entries * 4); E.vals_b.ensure(entries * 4);
   E.buckets.ensure(nbuckets * XYZZ_BYTES);
@@ -331,13 +333,13 @@ void msm_host(void* r_out, const void* coefs, const void* points, size_t len, bo
   E.d_scalars.ensure(sbytes);
   E.d_points.ensure(pbytes);
   cudaEvent_t t0 = E.ev[7], t1 = E.ev[8];
-  B200_CUDA_CHECK(cudaEventRecord(t0, E.stream));
+  B200_CUDA_CHECK(cudaEventRecord(t0, E.compute()));
   // scalars on the compute stream (digits + sort need only them); points on the copy stream so that the transfer
   // overlaps digit extraction and sorting.
-  B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, sbytes, cudaMemcpyHostToDevice, E.stream));
+  B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, sbytes, cudaMemcpyHostToDevice, E.compute()));
   B200_CUDA_CHECK(cudaMemcpyAsync(E.d_points.ptr, points, pbytes, cudaMemcpyHostToDevice, E.copy_stream));
   B200_CUDA_CHECK(cudaEventRecord(E.ev_points_ready, E.copy_stream));
-  B200_CUDA_CHECK(cudaEventRecord(t1, E.stream));
+  B200_CUDA_CHECK(cudaEventRecord(t1, E.compute()));
   HP r = msm_device<C>(E, E.d_scalars.ptr, E.d_points.ptr, len, fr_mont, 0, 0, -1, E.ev_points_ready);
   if (E.collect_timing) cudaEventElapsedTime(&E.stats.ms_h2d, t0, t1);
   write_result<C>(r_out, r, kind);

@@ -1,0 +1,69 @@
+"""One MSM split over several GPUs (one process per GPU, torch.distributed).
+
+The reference has no multi-device path; its closest construct is "MSM-level parallelism"
+(reference constantine/math/elliptic/ec_multi_scalar_mul_parallel.nim:386-431, msmAffine_vartime_parallel_split):
+cut the N (coef, point) pairs into balanced chunks, run one sub-MSM per chunk, add the partial results. Here a chunk
+is a rank: every rank runs the single-GPU engine on its shard and the <= world_size partial points (raw XYZZ, a few
+hundred bytes each) are exchanged with ONE all_gather (NCCL over NVLink on GPUs, gloo in the CPU tests) and summed on
+the host of every rank. An elliptic-curve addition is not an NCCL reduction op, hence gather-then-add.
+
+Window sharding (north star) is the alternative when every rank already holds all N pairs: rank g owns a contiguous
+range of windows and returns sum_{w in range} 2^(c w) S_w; the combination step is identical.
+"""
+import ctypes
+from typing import Callable, Optional, Tuple
+
+from . import msm as _msm
+from .curves import CURVES, CurveParams
+
+
+def balanced_chunk(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """[lo, hi) of chunk `rank` when n items are split into `world` chunks whose sizes differ by at most one
+    (same contract as the reference's balancedChunksPrioNumber, constantine/threadpool/partitioners.nim:44)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def window_range(num_windows: int, world: int, rank: int) -> Tuple[int, int]:
+    return balanced_chunk(num_windows, world, rank)
+
+
+def _all_gather_bytes(payload: bytes, group=None, device=None) -> list:
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    t = torch.frombuffer(bytearray(payload), dtype=torch.uint8)
+    if device is not None:
+        t = t.to(device)
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t, group=group)
+    return [bytes(o.cpu().numpy().tobytes()) for o in outs]
+
+
+def combine_partials(curve, partials: list, out=_msm.OUT_JAC) -> bytes:
+    cv = curve if isinstance(curve, CurveParams) else CURVES[curve]
+    return _msm.sum_partials(cv, b"".join(partials), len(partials), out=out)
+
+
+def msm_point_sharded(curve, local_partial_xyzz: bytes, group=None, device=None, out=_msm.OUT_JAC) -> bytes:
+    """Given this rank's raw XYZZ partial (MSM over its shard of the points), return the full MSM on every rank."""
+    parts = _all_gather_bytes(local_partial_xyzz, group=group, device=device)
+    return combine_partials(curve, parts, out=out)
+
+
+def msm_sharded_device(curve, d_coefs: int, d_points: int, n_local: int, group=None, device=None, out=_msm.OUT_JAC,
+                       fr_mont=False, windows: Optional[Tuple[int, int]] = None, force_c: int = 0,
+                       local_msm: Optional[Callable] = None) -> bytes:
+    """Full sharded MSM: local engine call on device-resident shard + all_gather + host combine.
+
+    `windows` = (begin, end) switches to window sharding (d_coefs/d_points then hold ALL pairs).
+    `local_msm` lets the CPU tests substitute the local engine call (no GPU there)."""
+    cv = curve if isinstance(curve, CurveParams) else CURVES[curve]
+    wb, we = windows if windows is not None else (0, -1)
+    if local_msm is None:
+        part = _msm.msm_device_ptrs(cv, d_coefs, d_points, n_local, out=_msm.OUT_XYZZ, fr_mont=fr_mont, force_c=force_c,
+                                    win_begin=wb, win_end=we)
+    else:
+        part = local_msm(cv, d_coefs, d_points, n_local)
+    return msm_point_sharded(cv, part, group=group, device=device, out=out)

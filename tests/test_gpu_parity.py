@@ -1,0 +1,244 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the oracle / golden vectors / closed forms.
+Bit-exact bar: integer work -- equality of the affine-normalised result (the reference's own notion of equality,
+tests/parallel/t_ec_template_parallel.nim:188)."""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+from helpers import CURVES, case_inputs, pack, point_pool, pyref, xyzz_bytes_to_affine
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def M():
+    from constantine_b200 import msm
+    return msm
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from constantine_b200 import _lib
+    return _lib.load()
+
+
+@pytest.fixture(scope="module")
+def tp(M):
+    t = M.Threadpool.new(2)
+    yield t
+    t.shutdown()
+
+
+# ------------------------------------------------------------------ kernels: field and point primitives
+def test_field_kernels_vs_oracle(lib, oracle_lib):
+    """fe_mul / add / sub / neg / dbl kernels on 2^16 random pairs per field + edge values, vs the oracle's C restatement
+    (and through it the exact tier, tests/test_oracle_golden.py)."""
+    from constantine_b200.curves import FIELDS
+    ids = {"bls12_381_fp": 0, "bn254_snarks_fp": 1, "pallas_fp": 2, "vesta_fp": 3, "bls12_381_fr": 4, "bn254_snarks_fr": 5,
+           "pallas_fr": 6, "vesta_fr": 7}
+    r = random.Random(11)
+    for name, fid in ids.items():
+        f = FIELDS[name]
+        n = 1 << 16
+        edge = [0, 1, f.modulus - 1, f.modulus - 2, f.one_mont, (1 << (f.bits - 1)) % f.modulus]
+        a = edge + [r.randrange(f.modulus) for _ in range(64)]
+        b = list(reversed(edge)) + [r.randrange(f.modulus) for _ in range(64)]
+        ab = b"".join(x.to_bytes(f.nbytes, "little") for x in a)
+        bb = b"".join(x.to_bytes(f.nbytes, "little") for x in b)
+        # bulk random residues straight from numpy (reduced by clearing the top bits: < 2^(bits-1) < p)
+        rng = np.random.default_rng(fid)
+        bulk_a = rng.integers(0, 256, size=(n, f.nbytes), dtype=np.uint8)
+        bulk_b = rng.integers(0, 256, size=(n, f.nbytes), dtype=np.uint8)
+        top = (f.bits - 1) % 8
+        bulk_a[:, -1] &= (1 << top) - 1
+        bulk_b[:, -1] &= (1 << top) - 1
+        ab += bulk_a.tobytes()
+        bb += bulk_b.tobytes()
+        cnt = len(ab) // f.nbytes
+        for op in range(5):
+            out = ctypes.create_string_buffer(len(ab))
+            assert lib.ctt_b200_test_field_op(fid, op, out, ab, bb, cnt) == 0
+            want = oracle_lib.fp_op(f, op if op < 4 else 1, ab, bb if op < 4 else ab, cnt)
+            assert out.raw == want, (name, op)
+
+
+@pytest.mark.parametrize("curve", list(CURVES))
+def test_point_kernels_vs_exact(lib, curve, rng):
+    """XYZZ mixed add / add / double incl. P+P, P-P and infinity operands vs the exact tier."""
+    cv = CURVES[curve]
+    ks, pool = point_pool(cv)
+    P = [pool[i] for i in range(24)] + [pool[0], pool[1], None, pool[2], None]
+    Q = [pool[i + 24] for i in range(24)] + [pool[0], pyref.ec_neg(pool[1], cv), pool[3], None, None]
+    n = len(P)
+    pb = b"".join(pyref.aff_to_bytes(x, cv) for x in P)
+    qb = b"".join(pyref.aff_to_bytes(x, cv) for x in Q)
+    dbl = lambda A: pyref.ec_add(A, A, cv)
+    expect = {0: lambda A, B: pyref.ec_add(A, B, cv), 1: lambda A, B: dbl(A), 2: lambda A, B: pyref.ec_add(dbl(A), dbl(B), cv),
+              3: lambda A, B: pyref.ec_add(dbl(A), B, cv), 4: lambda A, B: dbl(dbl(A))}
+    for op, fn in expect.items():
+        out = ctypes.create_string_buffer(n * 4 * cv.coord_bytes)
+        assert lib.ctt_b200_test_ec_op(cv.curve_id, op, out, pb, qb, n) == 0
+        for i in range(n):
+            got = xyzz_bytes_to_affine(out.raw[i * 4 * cv.coord_bytes:(i + 1) * 4 * cv.coord_bytes], cv)
+            assert got == fn(P[i], Q[i]), (curve, op, i)
+
+
+# ------------------------------------------------------------------ golden vectors through the reference's C symbols
+def test_eip2537_vectors_through_c_abi(kat, M, tp):
+    for case in kat["eip2537"]:
+        cv, ks, pts, want = case_inputs(case)
+        cb, pb = pack(cv, ks, pts)
+        got = M.multi_scalar_mul_vartime_parallel(tp, cv, cb, pb, len(ks), out="jac")
+        assert pyref.jac_bytes_to_affine(got, cv) == want, case["name"]
+        got = M.multi_scalar_mul_vartime(cv, cb, pb, len(ks), out="prj")
+        assert pyref.prj_bytes_to_affine(got, cv) == want, case["name"]
+
+
+def test_sage_vector_sums_through_c_abi(kat, M, tp):
+    for case in kat["sage_scalar_mul"]:
+        cv, ks, pts, want = case_inputs(case)
+        cb, pb = pack(cv, ks, pts)
+        assert pyref.jac_bytes_to_affine(M.multi_scalar_mul_vartime_parallel(tp, cv, cb, pb, len(ks)), cv) == want, case["name"]
+        cbm, _ = pack(cv, [k % cv.fr.modulus for k in ks], pts, fr_mont=True)
+        got = M.multi_scalar_mul_vartime_parallel(tp, cv, cbm, pb, len(ks), out="prj", coef_kind="fr")
+        assert pyref.prj_bytes_to_affine(got, cv) == want, case["name"]
+
+
+# ------------------------------------------------------------------ seeded random inputs vs the oracle
+@pytest.mark.parametrize("curve", list(CURVES))
+def test_sizes_vs_oracle(M, tp, oracle_lib, curve):
+    """N in {1..8, 16, 32, 64, 128, 1024, 2048, 16384} (reference tests/parallel/t_ec_shortw_jac_g1_msm_parallel.nim:17-29),
+    scalars uniform over the declared width (>= r allowed)."""
+    cv = CURVES[curve]
+    r = random.Random(hash(curve) & 0xFFFF)
+    _, pool = point_pool(cv)
+    sizes = [1, 2, 3, 4, 5, 6, 7, 8, 16, 32, 64, 128, 1024, 2048] + ([16384] if cv.ext_degree == 1 else [4096])
+    for n in sizes:
+        pts = [pool[r.randrange(len(pool))] for _ in range(n)]
+        ks = [r.getrandbits(cv.scalar_bits) for _ in range(n)]
+        cb, pb = pack(cv, ks, pts)
+        want = pyref.jac_bytes_to_affine(oracle_lib.msm(cv, cb, pb, n), cv)
+        assert pyref.jac_bytes_to_affine(M.multi_scalar_mul_vartime_parallel(tp, cv, cb, pb, n), cv) == want, (curve, n)
+
+
+@pytest.mark.parametrize("curve", list(CURVES))
+def test_edge_cases_vs_exact(M, tp, curve, rng):
+    """SURVEY.md Appendix E."""
+    cv = CURVES[curve]
+    _, pool = point_pool(cv)
+    P, Q = pool[0], pool[1]
+    r = cv.fr.modulus
+    top = (1 << cv.scalar_bits) - 1
+    cases = {
+        "len 0": ([], []),
+        "zero scalar": ([0], [P]), "one": ([1], [P]), "infinity point": ([rng.getrandbits(200)], [None]),
+        "inf + inf": ([3, 4], [None, None]), "P + P": ([7, 7], [P, P]), "P - P": ([9, 9], [P, pyref.ec_neg(P, cv)]),
+        "all equal points": ([rng.getrandbits(cv.scalar_bits) for _ in range(300)], [P] * 300),
+        "all equal points and scalars": ([12345] * 257, [Q] * 257),
+        "scalars >= r": ([r, r + 1, top], [P, Q, P]), "all-ones": ([top], [Q]),
+        "long 0/1 runs": ([int("1" * 100 + "0" * 60 + "1" * 90, 2), int("10" * 120, 2)] * 20, [P, Q] * 20),
+        "cancels to infinity": ([5, 5, 11, r - 11], [P, pyref.ec_neg(P, cv), Q, Q]),
+    }
+    for name, (ks, pts) in cases.items():
+        cb, pb = pack(cv, ks, pts)
+        want = pyref.msm_naive_fast(ks, pts, cv)
+        got = M.multi_scalar_mul_vartime_parallel(tp, cv, cb or b"\0" * 32, pb or bytes(cv.aff_bytes), len(ks))
+        assert pyref.jac_bytes_to_affine(got, cv) == want, (curve, name)
+
+
+def test_every_window_size_same_point(M, lib, rng):
+    """forced c = 2..20 incl. c | 255 (extra top window) -- device-resident entry + window-range partial sums"""
+    import torch
+    cv = CURVES["bls12_381_g1"]
+    _, pool = point_pool(cv)
+    n = 1500
+    pts = [pool[rng.randrange(len(pool))] for _ in range(n)]
+    ks = [rng.getrandbits(255) | (1 << 254) for _ in range(n)]
+    cb, pb = pack(cv, ks, pts)
+    want = pyref.msm_naive_fast(ks, pts, cv)
+    d_c = torch.frombuffer(bytearray(cb), dtype=torch.uint8).cuda()
+    d_p = torch.frombuffer(bytearray(pb), dtype=torch.uint8).cuda()
+    torch.cuda.synchronize()
+    for c in (2, 3, 5, 8, 11, 13, 15, 16, 17, 20):
+        got = M.msm_device_ptrs(cv, d_c.data_ptr(), d_p.data_ptr(), n, force_c=c)
+        assert pyref.jac_bytes_to_affine(got, cv) == want, c
+        W = 255 // c + 1
+        cut = W // 3
+        parts = b"".join(M.msm_device_ptrs(cv, d_c.data_ptr(), d_p.data_ptr(), n, out=M.OUT_XYZZ, force_c=c, win_begin=a, win_end=b)
+                         for a, b in ((0, cut), (cut, W - 1), (W - 1, W)))
+        assert pyref.jac_bytes_to_affine(M.sum_partials(cv, parts, 3), cv) == want, ("window ranges", c)
+
+
+def test_cached_bases(M, oracle_lib, rng):
+    """device-resident bases (the C face of the reference ZAL's base caching)"""
+    cv = CURVES["bn254_snarks_g1"]
+    _, pool = point_pool(cv)
+    n = 3000
+    pts = [pool[rng.randrange(len(pool))] for _ in range(n)]
+    _, pb = pack(cv, [], pts)
+    bases = M.CachedBases(cv, pb, n)
+    for trial in range(3):
+        ks = [rng.getrandbits(254) for _ in range(n)]
+        cb, _ = pack(cv, ks, [])
+        want = pyref.jac_bytes_to_affine(oracle_lib.msm(cv, cb, pb, n), cv)
+        assert pyref.jac_bytes_to_affine(bases.msm(cb, n), cv) == want
+    bases.free()
+
+
+# ------------------------------------------------------------------ BASELINE sizes: size-independent properties
+def _gen_points(lib, cv, k):
+    gen = b"".join(cv.fp.to_mont(c).to_bytes(cv.fp.nbytes, "little") for coord in cv.gen for c in coord)
+    out = np.empty((len(k), cv.aff_bytes), dtype=np.uint8)
+    assert lib.ctt_b200_scalar_mul_u64(cv.curve_id, gen, k.ctypes.data, len(k), out.ctypes.data) == 0
+    return out
+
+
+def test_generator_hook_vs_exact(lib):
+    for cv in CURVES.values():
+        k = np.array([1, 2, 3, 0xFFFFFFFFFFFFFFFF, 0x123456789ABCDEF, 0], dtype=np.uint64)
+        pts = _gen_points(lib, cv, k)
+        for i, kk in enumerate(k):
+            assert pyref.aff_from_bytes(pts[i].tobytes(), cv) == pyref.ec_mul_fast(int(kk), cv.gen, cv)
+
+
+@pytest.mark.parametrize("curve,logn", [("bn254_snarks_g1", 8), ("bls12_381_g1", 16), ("bls12_381_g1", 20), ("pallas_ec", 20),
+                                        ("bls12_381_g2", 16)])
+def test_closed_form_at_baseline_sizes(M, lib, tp, curve, logn):
+    """points P_i = [k_i]G with known k_i  =>  MSM = [sum s_i k_i mod r] G  (the bug-366 construction generalised,
+    SURVEY.md 8c item 4) -- exact at any N, here at BASELINE.json's sizes; plus linearity MSM(s+t) = MSM(s) + MSM(t)."""
+    cv = CURVES[curve]
+    n = 1 << logn
+    rng = np.random.default_rng(logn * 7 + cv.curve_id)
+    k = rng.integers(1, 2**63, size=n, dtype=np.uint64)
+    pts = _gen_points(lib, cv, k)
+    scal = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    scal[:, 31] &= (1 << (cv.scalar_bits - 248)) - 1
+    s_int = [int.from_bytes(scal[i].tobytes(), "little") for i in range(n)]
+    total = sum(s * int(kk) for s, kk in zip(s_int, k)) % cv.fr.modulus
+    want = pyref.ec_mul_fast(total, cv.gen, cv)
+    got = M.multi_scalar_mul_vartime_parallel(tp, cv, scal, pts, n)
+    assert pyref.jac_bytes_to_affine(got, cv) == want
+    # linearity on the same bases: MSM(s) + MSM(t) == MSM(s + t mod r)
+    t_int = [int(x) for x in rng.integers(0, 2**62, size=n)]
+    tb = np.frombuffer(b"".join(x.to_bytes(32, "little") for x in t_int), dtype=np.uint8).reshape(n, 32)
+    st = np.frombuffer(b"".join(((a + b) % cv.fr.modulus).to_bytes(32, "little") for a, b in zip(s_int, t_int)), dtype=np.uint8).reshape(n, 32)
+    a = pyref.jac_bytes_to_affine(M.multi_scalar_mul_vartime_parallel(tp, cv, tb, pts, n), cv)
+    b = pyref.jac_bytes_to_affine(M.multi_scalar_mul_vartime_parallel(tp, cv, st, pts, n), cv)
+    assert pyref.ec_add(want, a, cv) == b
+
+
+def test_adversarial_distribution_large(M, lib, tp):
+    """N = 2^18 with every scalar equal (one bucket per window) and long-0/1-run scalars: the slice/fix-up scheme must
+    stay exact (and finish) under maximal skew (reference helpers/prng_unsafe.nim:198-287 distributions)."""
+    cv = CURVES["bls12_381_g1"]
+    n = 1 << 18
+    rng = np.random.default_rng(3)
+    k = rng.integers(1, 2**63, size=n, dtype=np.uint64)
+    pts = _gen_points(lib, cv, k)
+    ksum = int(k.astype(object).sum())
+    for s in (0x5555AAAA5555AAAA5555AAAA5555AAAA5555AAAA5555AAAA5555AAAA5555AAAA & ((1 << 255) - 1), int("1" * 120 + "0" * 70 + "1" * 65, 2), 1):
+        scal = np.frombuffer(s.to_bytes(32, "little") * n, dtype=np.uint8).reshape(n, 32)
+        want = pyref.ec_mul_fast((s * ksum) % cv.fr.modulus, cv.gen, cv)
+        assert pyref.jac_bytes_to_affine(M.multi_scalar_mul_vartime_parallel(tp, cv, scal, pts, n), cv) == want

@@ -1,0 +1,76 @@
+"""CPU: host-side logic of the product -- constants, byte layouts, partial-sum combination (host tail arithmetic),
+sharding helpers."""
+import ctypes
+
+import pytest
+
+from helpers import CURVES, affine_to_xyzz_bytes, point_pool, pyref, xyzz_bytes_to_affine
+
+
+def test_montgomery_constants_match_survey_appendix_a():
+    from constantine_b200.curves import FIELDS
+    exp = {
+        "bn254_snarks_fp": (2, 0x87d20782e4866389, 0x0e0a77c19a07df2f666ea36f7879462c0a78eb28f5c70b3dd35d438dc58f0d9d),
+        "bn254_snarks_fr": (2, 0xc2e1f593efffffff, 0x0e0a77c19a07df2f666ea36f7879462e36fc76959f60cd29ac96341c4ffffffb),
+        "bls12_381_fp": (3, 0x89f3fffcfffcfffd, 0x15f65ec3fa80e4935c071a97a256ec6d77ce5853705257455f48985753c758baebf4000bc40c0002760900000002fffd),
+        "bls12_381_fr": (1, 0xfffffffeffffffff, 0x1824b159acc5056f998c4fefecbc4ff55884b7fa0003480200000001fffffffe),
+        "pallas_fp": (1, 0x992d30ecffffffff, 0x3fffffffffffffffffffffffffffffff992c350be41914ad34786d38fffffffd),
+        "pallas_fr": (1, 0x8c46eb20ffffffff, 0x3fffffffffffffffffffffffffffffff992c350be34205675b2b3e9cfffffffd),
+    }
+    for name, (spare, inv, one) in exp.items():
+        f = FIELDS[name]
+        assert (f.spare_bits, f.m0ninv64, f.one_mont) == (spare, inv, one)
+    assert FIELDS["vesta_fp"].modulus == FIELDS["pallas_fr"].modulus and FIELDS["vesta_fr"].modulus == FIELDS["pallas_fp"].modulus
+
+
+def test_struct_sizes_match_reference_layout():
+    sizes = {"bls12_381_g1": (96, 144), "bn254_snarks_g1": (64, 96), "pallas_ec": (64, 96), "vesta_ec": (64, 96),
+             "bls12_381_g2": (192, 288), "bn254_snarks_g2": (128, 192)}
+    for name, (aff, jac) in sizes.items():
+        assert (CURVES[name].aff_bytes, CURVES[name].jac_bytes) == (aff, jac)
+
+
+@pytest.mark.parametrize("curve", list(CURVES))
+def test_sum_partials_is_the_group_sum(curve, rng):
+    """ctt_b200_sum_partials runs the product's host arithmetic (host_field.hpp: Montgomery CIOS on 64-bit limbs, XYZZ
+    add/double, XYZZ -> Jacobian / projective) -- checked against the exact tier, incl. P+P, P-P and infinity."""
+    from constantine_b200 import msm as M
+    cv = CURVES[curve]
+    _, pool = point_pool(cv)
+    P, Q = pool[3], pool[4]
+    sets = [[P, Q], [P, P], [P, pyref.ec_neg(P, cv)], [None, Q, None], [None], [pool[i] for i in range(8)], [P, P, P, Q, Q]]
+    for pts in sets:
+        want = None
+        for A in pts:
+            want = pyref.ec_add(want, A, cv)
+        raw = b"".join(affine_to_xyzz_bytes(A, cv) for A in pts)
+        assert pyref.jac_bytes_to_affine(M.sum_partials(cv, raw, len(pts), out=M.OUT_JAC), cv) == want
+        assert pyref.prj_bytes_to_affine(M.sum_partials(cv, raw, len(pts), out=M.OUT_PRJ), cv) == want
+        assert xyzz_bytes_to_affine(M.sum_partials(cv, raw, len(pts), out=M.OUT_XYZZ), cv) == want
+    # reference encodings of the neutral element: Jacobian (1,1,0), projective (0,1,0)
+    inf_j = M.sum_partials(cv, affine_to_xyzz_bytes(None, cv), 1, out=M.OUT_JAC)
+    inf_p = M.sum_partials(cv, affine_to_xyzz_bytes(None, cv), 1, out=M.OUT_PRJ)
+    cb = cv.coord_bytes
+    one = pyref.coord_to_bytes((1,) + (0,) * (cv.ext_degree - 1), cv.fp)
+    assert inf_j == one + one + bytes(cb)
+    assert inf_p == bytes(cb) + one + bytes(cb)
+
+
+def test_balanced_chunks():
+    from constantine_b200.sharded import balanced_chunk, window_range
+    for n in (0, 1, 7, 8, 1 << 20, (1 << 20) + 5):
+        for world in (1, 2, 3, 4, 8):
+            spans = [balanced_chunk(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert [window_range(16, 8, r) for r in range(8)] == [(2 * r, 2 * r + 2) for r in range(8)]
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from constantine_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
