@@ -134,6 +134,9 @@ B200_DEV Xyzz<T> xyzz_dbl(const Xyzz<T>& p) {
 // (keeps ptxas time and code size bounded: each is compiled once per coordinate type instead of once per call site).
 template <class T>
 __device__ __noinline__ void xyzz_dbl_affine_ni(Xyzz<T>& r, const Aff<T>& p) { r = xyzz_dbl_affine(p); }
+// by-value flavour for the hot kernel: the accumulator stays in registers, only the (rare) call site copies
+template <class T>
+__device__ __noinline__ Xyzz<T> xyzz_dbl_affine_val(Aff<T> p) { return xyzz_dbl_affine(p); }
 template <class T>
 __device__ __noinline__ void xyzz_dbl_ni(Xyzz<T>& r) { r = xyzz_dbl(r); }
 
@@ -150,7 +153,7 @@ B200_DEV void xyzz_madd(Xyzz<T>& acc, const Aff<T>& q) {
   T P = U2 - acc.x;
   T R = S2 - acc.y;
   if (P.is_zero()) {
-    if (R.is_zero()) xyzz_dbl_affine_ni(acc, q);
+    if (R.is_zero()) acc = xyzz_dbl_affine_val(q);
     else acc = Xyzz<T>::inf();
     return;
   }

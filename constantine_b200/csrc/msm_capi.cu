@@ -97,7 +97,8 @@ ctt_b200_bases* ctt_b200_bases_upload(int curve_id, const void* points, size_t l
   b->curve_id = curve_id;
   b->len = len;
   B200_CUDA_CHECK(cudaMalloc(&b->d_points, len * 2 * coord + 16));
-  B200_CUDA_CHECK(cudaMemcpy(b->d_points, points, len * 2 * coord, cudaMemcpyHostToDevice));
+  B200_CUDA_CHECK(cudaMemcpyAsync(b->d_points, points, len * 2 * coord, cudaMemcpyHostToDevice, E.stream));
+  B200_CUDA_CHECK(cudaStreamSynchronize(E.stream));
   return reinterpret_cast<ctt_b200_bases*>(b);
 }
 

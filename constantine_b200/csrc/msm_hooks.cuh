@@ -52,12 +52,13 @@ int run_test_field_op(int op, void* r, const void* a, const void* b, size_t coun
   size_t bytes = count * F::N64 * 8;
   void *da, *db, *dr;
   B200_CUDA_CHECK(cudaMalloc(&da, bytes + 16)); B200_CUDA_CHECK(cudaMalloc(&db, bytes + 16)); B200_CUDA_CHECK(cudaMalloc(&dr, bytes + 16));
-  B200_CUDA_CHECK(cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice));
-  B200_CUDA_CHECK(cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice));
+  B200_CUDA_CHECK(cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, E.stream));
+  B200_CUDA_CHECK(cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, E.stream));
   k_test_field_op<F><<<(unsigned)((count + 127) / 128), 128, 0, E.stream>>>(op, (uint32_t*)dr, (const uint32_t*)da, (const uint32_t*)db, count);
   B200_CUDA_CHECK(cudaGetLastError());
   B200_CUDA_CHECK(cudaStreamSynchronize(E.stream));
-  B200_CUDA_CHECK(cudaMemcpy(r, dr, bytes, cudaMemcpyDeviceToHost));
+  B200_CUDA_CHECK(cudaMemcpyAsync(r, dr, bytes, cudaMemcpyDeviceToHost, E.stream));
+  B200_CUDA_CHECK(cudaStreamSynchronize(E.stream));
   cudaFree(da); cudaFree(db); cudaFree(dr);
   return 0;
 }
@@ -71,12 +72,13 @@ int run_test_ec_op(int op, void* r, const void* p, const void* q, size_t count) 
   size_t in_bytes = count * 2 * C::COORD_BYTES, out_bytes = count * 4 * C::COORD_BYTES;
   void *dp, *dq, *dr;
   B200_CUDA_CHECK(cudaMalloc(&dp, in_bytes + 16)); B200_CUDA_CHECK(cudaMalloc(&dq, in_bytes + 16)); B200_CUDA_CHECK(cudaMalloc(&dr, out_bytes + 16));
-  B200_CUDA_CHECK(cudaMemcpy(dp, p, in_bytes, cudaMemcpyHostToDevice));
-  B200_CUDA_CHECK(cudaMemcpy(dq, q, in_bytes, cudaMemcpyHostToDevice));
+  B200_CUDA_CHECK(cudaMemcpyAsync(dp, p, in_bytes, cudaMemcpyHostToDevice, E.stream));
+  B200_CUDA_CHECK(cudaMemcpyAsync(dq, q, in_bytes, cudaMemcpyHostToDevice, E.stream));
   k_test_ec_op<T><<<(unsigned)((count + 63) / 64), 64, 0, E.stream>>>(op, (uint32_t*)dr, (const uint32_t*)dp, (const uint32_t*)dq, count);
   B200_CUDA_CHECK(cudaGetLastError());
   B200_CUDA_CHECK(cudaStreamSynchronize(E.stream));
-  B200_CUDA_CHECK(cudaMemcpy(r, dr, out_bytes, cudaMemcpyDeviceToHost));
+  B200_CUDA_CHECK(cudaMemcpyAsync(r, dr, out_bytes, cudaMemcpyDeviceToHost, E.stream));
+  B200_CUDA_CHECK(cudaStreamSynchronize(E.stream));
   cudaFree(dp); cudaFree(dq); cudaFree(dr);
   return 0;
 }
@@ -130,12 +132,13 @@ int run_scalar_mul_u64(const void* base_aff, const void* k, size_t count, void* 
   size_t pt = 2 * C::COORD_BYTES;
   void *db, *dk, *dout;
   B200_CUDA_CHECK(cudaMalloc(&db, pt + 16)); B200_CUDA_CHECK(cudaMalloc(&dk, count * 8 + 16)); B200_CUDA_CHECK(cudaMalloc(&dout, count * pt + 16));
-  B200_CUDA_CHECK(cudaMemcpy(db, base_aff, pt, cudaMemcpyHostToDevice));
-  B200_CUDA_CHECK(cudaMemcpy(dk, k, count * 8, cudaMemcpyHostToDevice));
+  B200_CUDA_CHECK(cudaMemcpyAsync(db, base_aff, pt, cudaMemcpyHostToDevice, E.stream));
+  B200_CUDA_CHECK(cudaMemcpyAsync(dk, k, count * 8, cudaMemcpyHostToDevice, E.stream));
   k_scalar_mul_u64<T><<<(unsigned)((count + 127) / 128), 128, 0, E.stream>>>((const uint32_t*)db, (const unsigned long long*)dk, count, (uint32_t*)dout);
   B200_CUDA_CHECK(cudaGetLastError());
   B200_CUDA_CHECK(cudaStreamSynchronize(E.stream));
-  B200_CUDA_CHECK(cudaMemcpy(out_aff, dout, count * pt, cudaMemcpyDeviceToHost));
+  B200_CUDA_CHECK(cudaMemcpyAsync(out_aff, dout, count * pt, cudaMemcpyDeviceToHost, E.stream));
+  B200_CUDA_CHECK(cudaStreamSynchronize(E.stream));
   cudaFree(db); cudaFree(dk); cudaFree(dout);
   return 0;
 }
