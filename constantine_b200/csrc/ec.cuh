@@ -138,6 +138,8 @@ __device__ __noinline__ void xyzz_dbl_affine_ni(Xyzz<T>& r, const Aff<T>& p) { r
 template <class T>
 __device__ __noinline__ Xyzz<T> xyzz_dbl_affine_val(Aff<T> p) { return xyzz_dbl_affine(p); }
 template <class T>
+__device__ __noinline__ Xyzz<T> xyzz_dbl_val(Xyzz<T> p) { return xyzz_dbl(p); }
+template <class T>
 __device__ __noinline__ void xyzz_dbl_ni(Xyzz<T>& r) { r = xyzz_dbl(r); }
 
 // acc += q  (q affine, finite or infinity): madd-2008-s, 8M + 2S on the generic path.
@@ -180,7 +182,7 @@ B200_DEV void xyzz_add(Xyzz<T>& acc, const Xyzz<T>& q) {
   T P = U2 - U1;
   T R = S2 - S1;
   if (P.is_zero()) {
-    if (R.is_zero()) xyzz_dbl_ni(acc);
+    if (R.is_zero()) acc = xyzz_dbl_val(acc);
     else acc = Xyzz<T>::inf();
     return;
   }

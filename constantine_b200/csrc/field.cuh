@@ -247,10 +247,15 @@ struct Fp {
   // a^(p-2) (Fermat). Off the hot path only (affine normalisation in the input generator / test hooks).
   __device__ __noinline__ Fp inv() const {
     Fp r = one(), b = *this;
+    uint32_t borrow = 2u;  // exponent p - 2, computed word by word with borrow (p's low word may be 1, e.g. Pasta)
+    uint32_t w = 0;
 #pragma unroll 1
     for (int i = 0; i < 32 * N; i++) {
-      uint32_t w = F::P(i >> 5);
-      if ((i >> 5) == 0) w -= 2u;  // p is odd and its low word is > 2 for every field here
+      if ((i & 31) == 0) {
+        uint32_t pw = F::P(i >> 5);
+        w = pw - borrow;
+        borrow = (pw < borrow) ? 1u : 0u;
+      }
       if ((w >> (i & 31)) & 1u) fe_mul_ni(r.l, r.l, b.l);
       fe_mul_ni(b.l, b.l, b.l);
     }

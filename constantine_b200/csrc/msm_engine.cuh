@@ -55,7 +55,7 @@ using Bn254G2 = CurveDesc<Bn254SnarksFp, Bn254SnarksFr, 2>;
 struct Tuning {
   int force_c = 0;            // 0 = cost model
   int reduce_chunk = 16;      // L: buckets per bucket-reduce thread
-  int sum_group = 16;         // G: fan-in of the tree sum
+  int sum_group = 32;         // (fixed) fan-in of the warp-butterfly row sums
 };
 
 struct Stats {               // filled per call; read back through ctt_b200_last_stats
@@ -248,47 +248,57 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
     // a single remaining slice never continues a previous one: its runs were all added to their buckets.
   }
   if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[4], s));
-  // 5. bucket reduce + tree sum
+  // 5. bucket reduce: chunked running sums, then warp-butterfly row sums down to <= 4 points per window
+  constexpr bool INL = (T::WORDS <= 12);   // single-field coordinates: inline the point adds; Fp2: out-of-line (code size)
   uint32_t L = (uint32_t)E.tuning.reduce_chunk;
   if (L < 1) L = 1;
   uint32_t chunks = (B + L - 1) / L;
-  // keep at least ~8 warps per SM worth of chunk threads when the bucket count allows it
-  while (L > 1 && (size_t)chunks * nw < (size_t)E.sm_count * 256 && chunks < B) { L = (L + 1) / 2; chunks = (B + L - 1) / L; }
+  // small bucket counts: keep at least ~2 warps per SM worth of chunk threads
+  while (L > 1 && (size_t)chunks * nw < (size_t)E.sm_count * 64 && chunks < B) { L = (L + 1) / 2; chunks = (B + L - 1) / L; }
+  int nbits = 0;
+  while (nbits < 32 && ((uint64_t)(chunks - 1) * L >> nbits) != 0) nbits++;
   E.red_a.ensure((size_t)chunks * nw * XYZZ_BYTES);
+  E.red_b.ensure((size_t)chunks * nw * XYZZ_BYTES);
   {
     size_t threads = (size_t)chunks * nw;
-    dim3 block(128), grid((unsigned)((threads + 127) / 128));
-    k_bucket_reduce<T><<<grid, block, 0, s>>>((const uint32_t*)E.buckets.ptr, B, L, chunks, (uint32_t)nw, (uint32_t*)E.red_a.ptr);
-    launches++;
+    dim3 block(64), grid((unsigned)((threads + 63) / 64));
+    k_bucket_reduce<T, INL><<<grid, block, 0, s>>>((const uint32_t*)E.buckets.ptr, B, L, chunks, (uint32_t)nw, (uint32_t*)E.red_a.ptr,
+                                                    (uint32_t*)E.red_b.ptr);
+    k_chunk_offset<T, INL><<<grid, block, 0, s>>>((uint32_t*)E.red_a.ptr, (const uint32_t*)E.red_b.ptr, L, chunks, (uint32_t)nw, nbits);
+    launches += 2;
   }
   uint32_t row = chunks;
-  const uint32_t G = (uint32_t)(E.tuning.sum_group < 2 ? 2 : E.tuning.sum_group);
   DeviceBuffer* src = &E.red_a;
   DeviceBuffer* dst = &E.red_b;
-  while (row > 1) {
-    uint32_t out_row = (row + G - 1) / G;
+  while (row > 4) {
+    uint32_t out_row = (row + 31) / 32;
     dst->ensure((size_t)out_row * nw * XYZZ_BYTES);
-    size_t threads = (size_t)out_row * nw;
-    dim3 block(128), grid((unsigned)((threads + 127) / 128));
-    k_sum_groups<T><<<grid, block, 0, s>>>((const uint32_t*)src->ptr, row, G, out_row, (uint32_t)nw, (uint32_t*)dst->ptr);
+    size_t warps = (size_t)out_row * nw;
+    dim3 block(128), grid((unsigned)((warps * 32 + 127) / 128));
+    k_row_sum_warp<T, INL><<<grid, block, 0, s>>>((const uint32_t*)src->ptr, row, out_row, (uint32_t)nw, (uint32_t*)dst->ptr);
     launches++;
     row = out_row;
     DeviceBuffer* tmp = src; src = dst; dst = tmp;
   }
   if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[5], s));
-  // 6. window sums -> host, Horner tail
-  const size_t out_bytes = (size_t)nw * XYZZ_BYTES;
+  // 6. per-window partial sums (<= 4 each) -> host; finish the sums and run the Horner tail there
+  const size_t out_bytes = (size_t)nw * row * XYZZ_BYTES;
   if (out_bytes > E.h_result_cap) { fprintf(stderr, "[ctt_b200_msm] FATAL: result staging too small\n"); abort(); }
   B200_CUDA_CHECK(cudaMemcpyAsync(E.h_result, src->ptr, out_bytes, cudaMemcpyDeviceToHost, s));
   B200_CUDA_CHECK(cudaStreamSynchronize(s));
   static_assert(sizeof(HP) == XYZZ_BYTES, "host/device XYZZ layout");
-  const HP* sums = reinterpret_cast<const HP*>(E.h_result);
+  const HP* parts = reinterpret_cast<const HP*>(E.h_result);
+  auto window_sum = [&](int w) {
+    HP a = parts[(size_t)w * row];
+    for (uint32_t i = 1; i < row; i++) a = host::xyzz_add(a, parts[(size_t)w * row + i]);
+    return a;
+  };
   // r = sum_w 2^(c*w) S_w  for w in [win_begin, win_end):  Horner from the top window of the range, then shift by c*win_begin
   // (reference ec_multi_scalar_mul_parallel.nim:198-203: c doublings + one addition per window).
-  HP r = sums[nw - 1];
+  HP r = window_sum(nw - 1);
   for (int w = nw - 2; w >= 0; w--) {
     for (int i = 0; i < c; i++) r = host::xyzz_dbl(r);
-    r = host::xyzz_add(r, sums[w]);
+    r = host::xyzz_add(r, window_sum(w));
   }
   for (int i = 0; i < c * plan.win_begin; i++) r = host::xyzz_dbl(r);
   if (E.collect_timing) {

@@ -97,42 +97,73 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
 constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 
 // Slice kernel over the sorted (key, point-ref) list.  `no_key` = first key value that means "no bucket".
+//
+// A run of equal keys that starts inside a slice is owned by that slice's thread, which stores the bucket. A run that
+// continues from the previous slice ("head") cannot be stored by this thread. Heads are handed to the previous lane of
+// the same warp through shared memory and added into that lane's last run before it is stored (one extra XYZZ add per
+// warp), so only heads whose predecessor lives in another warp -- or is itself a single-run continuation slice --
+// are spilled to the global partial list that k_fixup resolves.
 template <class T, int K>
 __global__ void __launch_bounds__(128) k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                                     size_t total, uint32_t no_key, const uint32_t* __restrict__ points,
                                                     uint32_t* buckets, uint32_t* part_pts, uint32_t* part_keys, size_t num_slices) {
+  __shared__ uint32_t head_smem[128 * 4 * T::WORDS];
+  const unsigned lane = threadIdx.x & 31u;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= num_slices) return;
+  const bool live = t < num_slices;
   size_t base = t * K;
-  uint32_t prev_key = (t > 0) ? keys[base - 1] : KEY_NONE;
+  uint32_t prev_key = (live && t > 0) ? keys[base - 1] : KEY_NONE;
   uint32_t cur_key = KEY_NONE;
-  bool wrote_partial = false;
+  bool head_valid = false;     // first run continues the previous slice (its sum is parked in head_smem[threadIdx.x])
+  bool first_run = true;
   Xyzz<T> acc = Xyzz<T>::inf();
+  if (live) {
 #pragma unroll 1
-  for (int j = 0; j < K; j++) {
-    size_t idx = base + j;
-    if (idx >= total) break;
-    uint32_t key = keys[idx];
-    if (key >= no_key) break;  // zero digits are sorted to the tail: nothing left in this slice
-    uint32_t v = vals[idx];
-    Aff<T> p = load_affine<T>(points, v & 0x7FFFFFFFu);
-    if (!p.is_inf()) p.y.cneg((v >> 31) != 0);
-    if (key != cur_key) {
-      if (cur_key != KEY_NONE) {
-        if (cur_key == prev_key) { store_xyzz(part_pts, t, acc); part_keys[t] = cur_key; wrote_partial = true; }
-        else store_xyzz(buckets, (size_t)cur_key, acc);
+    for (int j = 0; j < K; j++) {
+      size_t idx = base + j;
+      if (idx >= total) break;
+      uint32_t key = keys[idx];
+      if (key >= no_key) break;  // zero digits are sorted to the tail: nothing left in this slice
+      uint32_t v = vals[idx];
+      Aff<T> p = load_affine<T>(points, v & 0x7FFFFFFFu);
+      if (!p.is_inf()) p.y.cneg((v >> 31) != 0);
+      if (key != cur_key) {
+        if (cur_key != KEY_NONE) {
+          if (first_run && cur_key == prev_key) { store_xyzz(head_smem, threadIdx.x, acc); head_valid = true; }
+          else store_xyzz(buckets, (size_t)cur_key, acc);
+          first_run = false;
+        }
+        cur_key = key;
+        acc = Xyzz<T>::from_affine(p);
+      } else {
+        xyzz_madd(acc, p);
       }
-      cur_key = key;
-      acc = Xyzz<T>::from_affine(p);
-    } else {
-      xyzz_madd(acc, p);
     }
   }
-  if (cur_key != KEY_NONE) {
-    if (cur_key == prev_key) { store_xyzz(part_pts, t, acc); part_keys[t] = cur_key; wrote_partial = true; }
-    else store_xyzz(buckets, (size_t)cur_key, acc);
+  // the last run of the slice is still in `acc`
+  const bool has_run = cur_key != KEY_NONE;
+  const bool last_is_head = has_run && first_run && cur_key == prev_key;  // single-run slice continuing its predecessor
+  if (last_is_head) { store_xyzz(head_smem, threadIdx.x, acc); head_valid = true; }
+  const bool absorber = has_run && !last_is_head;                        // owns the bucket of its last run
+  __syncwarp();
+  const bool prev_absorbs = __shfl_up_sync(0xFFFFFFFFu, absorber ? 1 : 0, 1) != 0 && lane > 0;
+  const bool next_has_head = __shfl_down_sync(0xFFFFFFFFu, head_valid ? 1 : 0, 1) != 0 && lane < 31;
+  if (absorber) {
+    if (next_has_head) {
+      Xyzz<T> h = load_xyzz<T>(head_smem, threadIdx.x + 1);
+      xyzz_add(acc, h);
+    }
+    store_xyzz(buckets, (size_t)cur_key, acc);
   }
-  if (!wrote_partial) part_keys[t] = KEY_NONE;
+  if (live) {
+    if (head_valid && !prev_absorbs) {
+      Xyzz<T> h = load_xyzz<T>(head_smem, threadIdx.x);
+      store_xyzz(part_pts, t, h);
+      part_keys[t] = prev_key;
+    } else {
+      part_keys[t] = KEY_NONE;
+    }
+  }
 }
 
 // Fix-up level: input = list of (key, XYZZ) partials in slice order (KEY_NONE entries are holes).  Equal keys are
@@ -174,13 +205,24 @@ __global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ in_k
 
 // ------------------------------------------------------------------------------------------- bucket reduction
 // Window sum  S = sum_{j=0}^{B-1} (j+1) * bucket[j]   (reference ec_multi_scalar_mul.nim:186-197 bucketReduce computes
-// the same value with one serial running sum).  Here B buckets are cut into T = B/L chunks of L consecutive buckets:
+// the same value with one serial running sum).  Here B buckets are cut into chunks of L consecutive buckets:
 //   chunk t:  run = sum_i b[tL+i],  acc = sum_i (i+1) b[tL+i]  (running sum, 2 adds per bucket)
 //   S = sum_t ( acc_t + (t*L) * run_t )
-// (t*L)*run_t is a <= 20-bit double-and-add.  Output: one point per chunk; k_sum_groups adds them up.
-template <class T>
-__global__ void __launch_bounds__(128) k_bucket_reduce(const uint32_t* buckets, uint32_t buckets_per_window, uint32_t L,
-                                                       uint32_t chunks_per_window, uint32_t num_windows, uint32_t* out) {
+// (t*L)*run_t is a double-and-add over `nbits` bits (uniform loop bound). One point per chunk comes out;
+// k_row_sum_warp adds them up with warp butterflies.
+template <class T, bool INL>
+B200_DEV void padd(Xyzz<T>& a, const Xyzz<T>& b) {
+  if constexpr (INL) xyzz_add(a, b); else xyzz_add_ni(a, b);
+}
+template <class T, bool INL>
+B200_DEV void pdbl(Xyzz<T>& a) {
+  if constexpr (INL) a = xyzz_dbl(a); else xyzz_dbl_ni(a);
+}
+
+template <class T, bool INL>
+__global__ void __launch_bounds__(64) k_bucket_reduce(const uint32_t* buckets, uint32_t buckets_per_window, uint32_t L,
+                                                      uint32_t chunks_per_window, uint32_t num_windows, uint32_t* out_acc,
+                                                      uint32_t* out_run) {
   size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= (size_t)chunks_per_window * num_windows) return;
   uint32_t w = (uint32_t)(g / chunks_per_window), t = (uint32_t)(g % chunks_per_window);
@@ -190,38 +232,57 @@ __global__ void __launch_bounds__(128) k_bucket_reduce(const uint32_t* buckets, 
 #pragma unroll 1
   for (int i = (int)cnt - 1; i >= 0; i--) {
     Xyzz<T> b = load_xyzz<T>(buckets, first + i);
-    xyzz_add_ni(run, b);
-    xyzz_add_ni(acc, run);
+    padd<T, INL>(run, b);
+    padd<T, INL>(acc, run);
   }
-  uint32_t off = t * L;
-  if (off != 0 && !run.is_inf()) {
-    Xyzz<T> m = Xyzz<T>::inf();
-#pragma unroll 1
-    for (int bit = 31 - __clz(off); bit >= 0; bit--) {
-      xyzz_dbl_ni(m);
-      if ((off >> bit) & 1u) xyzz_add_ni(m, run);
-    }
-    xyzz_add_ni(acc, m);
-  }
-  store_xyzz(out, g, acc);
+  store_xyzz(out_acc, g, acc);
+  store_xyzz(out_run, g, run);
 }
 
-// out[g] = sum_{i < G} in[g*G + i]  within each window's row of `row_len` entries (rows are padded to groups)
-template <class T>
-__global__ void __launch_bounds__(128) k_sum_groups(const uint32_t* in, uint32_t row_len, uint32_t G, uint32_t out_row_len,
-                                                    uint32_t num_rows, uint32_t* out) {
+// acc[g] += (t*L) * run[g]   -- double-and-add over `nbits` bits (uniform trip count; lanes whose bit is clear idle)
+template <class T, bool INL>
+__global__ void __launch_bounds__(64) k_chunk_offset(uint32_t* acc_io, const uint32_t* run_in, uint32_t L, uint32_t chunks_per_window,
+                                                     uint32_t num_windows, int nbits) {
   size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= (size_t)out_row_len * num_rows) return;
-  uint32_t row = (uint32_t)(g / out_row_len), o = (uint32_t)(g % out_row_len);
-  Xyzz<T> acc = Xyzz<T>::inf();
+  if (g >= (size_t)chunks_per_window * num_windows) return;
+  const uint32_t off = (uint32_t)(g % chunks_per_window) * L;
+  if (off == 0) return;
+  Xyzz<T> run = load_xyzz<T>(run_in, g);
+  Xyzz<T> m = Xyzz<T>::inf();
 #pragma unroll 1
-  for (uint32_t i = 0; i < G; i++) {
-    uint32_t src = o * G + i;
-    if (src >= row_len) break;
-    Xyzz<T> q = load_xyzz<T>(in, (size_t)row * row_len + src);
-    xyzz_add_ni(acc, q);
+  for (int bit = nbits - 1; bit >= 0; bit--) {
+    pdbl<T, INL>(m);
+    if ((off >> bit) & 1u) padd<T, INL>(m, run);
   }
-  store_xyzz(out, g, acc);
+  Xyzz<T> acc = load_xyzz<T>(acc_io, g);
+  padd<T, false>(acc, m);
+  store_xyzz(acc_io, g, acc);
+}
+
+// One warp per group of 32 consecutive entries of a row: out[row][g] = sum_{i<32} in[row][32 g + i] (butterfly over
+// shuffles: 5 dependent additions instead of 31).
+template <class T, bool INL>
+__global__ void __launch_bounds__(128) k_row_sum_warp(const uint32_t* in, uint32_t row_len, uint32_t out_row_len, uint32_t num_rows,
+                                                      uint32_t* out) {
+  const unsigned lane = threadIdx.x & 31u;
+  size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= (size_t)out_row_len * num_rows) return;
+  uint32_t row = (uint32_t)(warp / out_row_len), o = (uint32_t)(warp % out_row_len);
+  uint32_t src = o * 32u + lane;
+  Xyzz<T> acc = (src < row_len) ? load_xyzz<T>(in, (size_t)row * row_len + src) : Xyzz<T>::inf();
+#pragma unroll 1
+  for (int d = 16; d >= 1; d >>= 1) {
+    Xyzz<T> other;
+#pragma unroll
+    for (int k = 0; k < T::WORDS; k++) {
+      other.x.set_word(k, __shfl_xor_sync(0xFFFFFFFFu, acc.x.word(k), d));
+      other.y.set_word(k, __shfl_xor_sync(0xFFFFFFFFu, acc.y.word(k), d));
+      other.zz.set_word(k, __shfl_xor_sync(0xFFFFFFFFu, acc.zz.word(k), d));
+      other.zzz.set_word(k, __shfl_xor_sync(0xFFFFFFFFu, acc.zzz.word(k), d));
+    }
+    padd<T, INL>(acc, other);
+  }
+  if (lane == 0) store_xyzz(out, warp, acc);
 }
 
 }  // namespace b200

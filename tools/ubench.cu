@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include "../constantine_b200/csrc/ec.cuh"
 #include "../constantine_b200/csrc/host_field.hpp"
+#include "../constantine_b200/csrc/field_rr.cuh"
 
 using namespace b200;
 
@@ -168,6 +169,99 @@ void bench_field(const char* name, int sms, double clock_ghz) {
   cudaFree(d_in); cudaFree(d_out);
 }
 
+// ---------------------------------------------------------------- reduced-radix (carry-free) multiplier prototype
+template <class R, class F>
+__global__ void k_rr_mul_chain(const uint32_t* in, uint32_t* out, int n, int iters) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t a[F::N], b[F::N];
+  for (int k = 0; k < F::N; k++) { a[k] = in[(size_t)(2 * i) * F::N + k]; b[k] = in[(size_t)(2 * i + 1) * F::N + k]; }
+  R x = R::from_abi(a), y = R::from_abi(b);
+  for (int k = 0; k < iters; k++) { x = x * y; y = y * x; }
+  for (int k = 0; k < R::PR::NL; k++) out[(size_t)i * R::PR::NL + k] = x.l[k];
+}
+
+template <class R, class F>
+__global__ void k_rr_mulps_chain(const uint32_t* in, uint32_t* out, int n, int iters) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t a[F::N], b[F::N];
+  for (int k = 0; k < F::N; k++) { a[k] = in[(size_t)(2 * i) * F::N + k]; b[k] = in[(size_t)(2 * i + 1) * F::N + k]; }
+  R x = R::from_abi(a), y = R::from_abi(b);
+  for (int k = 0; k < iters; k++) { x = x.mul_ps(y); y = y.mul_ps(x); }
+  for (int k = 0; k < R::PR::NL; k++) out[(size_t)i * R::PR::NL + k] = x.l[k];
+}
+
+template <class F, int W, int NL>
+void bench_rr(const char* name, int sms, double clock_ghz) {
+  typedef FpRR<F, W, NL> R;
+  typedef host::HFp<F> H;
+  const int n = sms * 2048, iters = 64;
+  std::vector<H> in(2 * n);
+  for (auto& v : in) v = rand_fe<F>();
+  uint32_t *d_in, *d_out;
+  CK(cudaMalloc(&d_in, sizeof(H) * 2 * n));
+  CK(cudaMalloc(&d_out, 4 * NL * (size_t)n));
+  CK(cudaMemcpy(d_in, in.data(), sizeof(H) * 2 * n, cudaMemcpyHostToDevice));
+  int threads = 128;
+  k_rr_mul_chain<R, F><<<(n + threads - 1) / threads, threads>>>(d_in, d_out, n, 2);
+  CK(cudaDeviceSynchronize());
+  {
+    cudaEvent_t f0, f1; cudaEventCreate(&f0); cudaEventCreate(&f1);
+    k_rr_mulps_chain<R, F><<<(n + threads - 1) / threads, threads>>>(d_in, d_out, n, 2);
+    cudaEventRecord(f0);
+    k_rr_mulps_chain<R, F><<<(n + threads - 1) / threads, threads>>>(d_in, d_out, n, iters);
+    cudaEventRecord(f1);
+    CK(cudaDeviceSynchronize());
+    float ms2; cudaEventElapsedTime(&ms2, f0, f1);
+    std::vector<uint32_t> o2((size_t)NL * n);
+    CK(cudaMemcpy(o2.data(), d_out, 4 * NL * (size_t)n, cudaMemcpyDeviceToHost));
+    k_rr_mul_chain<R, F><<<(n + threads - 1) / threads, threads>>>(d_in, d_out, n, iters);
+    CK(cudaDeviceSynchronize());
+    std::vector<uint32_t> o1((size_t)NL * n);
+    CK(cudaMemcpy(o1.data(), d_out, 4 * NL * (size_t)n, cudaMemcpyDeviceToHost));
+    size_t diff = 0; for (size_t q = 0; q < o1.size(); q++) diff += (o1[q] != o2[q]);
+    double per_s2 = (double)n * iters * 2 / (ms2 * 1e-3);
+    printf("{\"bench\":\"fe_mul_reduced_radix_product_scanning\",\"field\":\"%s\",\"W\":%d,\"limbs\":%d,\"limb_diffs_vs_operand_scanning\":%zu,\"ms\":%.4f,\"Gmul_per_s\":%.2f,\"clk_per_mul_per_sm\":%.1f}\n",
+           name, W, NL, diff, ms2, per_s2 * 1e-9, sms * clock_ghz * 1e9 / per_s2);
+  }
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  k_rr_mul_chain<R, F><<<(n + threads - 1) / threads, threads>>>(d_in, d_out, n, iters);
+  cudaEventRecord(e1);
+  CK(cudaDeviceSynchronize());
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  std::vector<uint32_t> out((size_t)NL * n);
+  CK(cudaMemcpy(out.data(), d_out, 4 * NL * (size_t)n, cudaMemcpyDeviceToHost));
+  // expected: host chain in the ABI Montgomery domain, then times 2^SHIFT (change of radix R -> R')
+  H two_shift = H::zero(); two_shift.l[0] = 1ull << R::PR::SHIFT;
+  H r2; for (int i = 0; i < F::N64; i++) r2.l[i] = F::R264(i);
+  H c = two_shift * r2;  // Montgomery form of 2^SHIFT
+  int bad = 0;
+  for (int i = 0; i < 512; i++) {
+    H x = in[2 * i], y = in[2 * i + 1];
+    for (int k = 0; k < iters; k++) { x = x * y; y = y * x; }
+    H want = x * c;
+    // device limbs (radix 2^W, value < 2p) -> integer -> canonical
+    unsigned __int128 acc = 0; int accbits = 0; uint64_t limbs[F::N64 + 1]; int li = 0;
+    for (int k = 0; k < F::N64 + 1; k++) limbs[k] = 0;
+    for (int k = 0; k < NL; k++) {
+      acc += (unsigned __int128)out[(size_t)i * NL + k] << accbits; accbits += W;
+      while (accbits >= 64 && li < F::N64 + 1) { limbs[li++] = (uint64_t)acc; acc >>= 64; accbits -= 64; }
+    }
+    if (li < F::N64 + 1) limbs[li++] = (uint64_t)acc;
+    H got; for (int k = 0; k < F::N64; k++) got.l[k] = limbs[k];
+    bool ok = limbs[F::N64] == 0;
+    for (int t = 0; t < 3 && H::geq_p(got.l); t++) H::sub_p(got.l);
+    if (!ok || !(got == want)) bad++;
+  }
+  double muls = (double)n * iters * 2;
+  double per_s = muls / (ms * 1e-3);
+  printf("{\"bench\":\"fe_mul_reduced_radix\",\"field\":\"%s\",\"W\":%d,\"limbs\":%d,\"mismatch_of_512\":%d,\"ms\":%.4f,\"Gmul_per_s\":%.2f,\"clk_per_mul_per_sm\":%.1f}\n",
+         name, W, NL, bad, ms, per_s * 1e-9, sms * clock_ghz * 1e9 / per_s);
+  cudaFree(d_in); cudaFree(d_out);
+}
+
 template <class F>
 void bench_madd(const char* name, int sms, double clock_ghz, const uint64_t* gx, const uint64_t* gy) {
   typedef Fp<F> T;
@@ -239,6 +333,11 @@ int main() {
   bench_field<Bn254SnarksFp>("bn254_snarks_fp", sms, clock_ghz);
   bench_field<PallasFp>("pallas_fp", sms, clock_ghz);
   bench_field<Bls12381Fr>("bls12_381_fr", sms, clock_ghz);
+  bench_rr<Bls12381Fp, 28, 14>("bls12_381_fp", sms, clock_ghz);
+  bench_rr<Bls12381Fp, 29, 14>("bls12_381_fp", sms, clock_ghz);
+  bench_rr<Bn254SnarksFp, 29, 9>("bn254_snarks_fp", sms, clock_ghz);
+  bench_rr<PallasFp, 29, 9>("pallas_fp", sms, clock_ghz);
+  bench_rr<PallasFp, 26, 10>("pallas_fp", sms, clock_ghz);
   {
     const uint64_t gx[6] = {0xfb3af00adb22c6bbull, 0x6c55e83ff97a1aefull, 0xa14e3a3f171bac58ull, 0xc3688c4f9774b905ull, 0x2695638c4fa9ac0full, 0x17f1d3a73197d794ull};
     const uint64_t gy[6] = {0x0caa232946c5e7e1ull, 0xd03cc744a2888ae4ull, 0x00db18cb2c04b3edull, 0xfcf5e095d5d00af6ull, 0xa09e30ed741d8ae4ull, 0x08b3f481e3aaa0f1ull};
