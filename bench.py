@@ -35,9 +35,12 @@ if ROOT not in sys.path:
 CURVE = "bls12_381_g1"
 INT_MACS_PER_POINT_ADD = 3300            # 11 field mults x (2*12^2 + 12) MACs, BLS12-381 G1
 ALGO_BYTES_PER_TERM = 128                # 32 B scalar + 96 B affine point
-# Measured on this pool's B200 (tools/ubench.cu, profiles/ubench_r1.jsonl): mad.wide.u32 issues at 63.7 /clk/SM
-# => 148 SMs x 63.7 x 1.965 GHz = 18.5e12 32x32->64 MACs/s.  (IMAD.WIDE with carry-in/out runs at half that.)
-INT_MAC_PEAK_PER_S = 18.52e12
+# Measured on this pool's B200 (tools/ubench.cu, profiles/ubench_r1.jsonl): the integer multiplier issues 63.4 IMAD /clk/SM,
+# i.e. one 32-bit result half per lane per pass; a full 32x32->64 multiply-accumulate (IMAD.WIDE.U32 with 64-bit addend
+# or carry, what mad.lo.cc/madc.hi.cc pairs compile to) takes two passes: measured 31.65 MAC/clk/SM
+# => 148 SMs x 31.65 x 1.965 GHz = 9.2e12 MACs/s.  (A carry-free reduced-radix multiplier was prototyped and is slower:
+# profiles/ubench_r1b.jsonl.)
+INT_MAC_PEAK_PER_S = 9.205e12
 
 
 def dist_env():
@@ -332,7 +335,7 @@ def main():
         "roofline": {"bound": "int32-mad (neither hbm nor tensor: see roofline_hbm)", "kernel": "k_accumulate",
                      "achieved": achieved / 1e12, "peak": INT_MAC_PEAK_PER_S / 1e12, "unit": "TMAC/s (32x32->64)",
                      "frac": achieved / INT_MAC_PEAK_PER_S, "traffic": None,
-                     "peak_source": "measured IMAD.WIDE issue rate, tools/ubench.cu -> profiles/ubench_r1.jsonl",
+                     "peak_source": "measured 32x32->64 MAC rate (IMAD.WIDE.U32.X chains, 31.65/clk/SM x 148 SM x 1.965 GHz), tools/ubench.cu -> profiles/ubench_r1.jsonl",
                      "algorithmic_work": f"{madds} bucket point-adds x {INT_MACS_PER_POINT_ADD} MACs per launch, {acc_ms:.3f} ms"},
         "roofline_hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                          "traffic": None, "peak_source": hbm_src, "algorithmic_bytes": algo_bytes},

@@ -155,7 +155,10 @@ B200_DEV void xyzz_madd(Xyzz<T>& acc, const Aff<T>& q) {
   T P = U2 - acc.x;
   T R = S2 - acc.y;
   if (P.is_zero()) {
-    if (R.is_zero()) acc = xyzz_dbl_affine_val(q);
+    if (R.is_zero()) {
+      if constexpr (T::WORDS <= 12) acc = xyzz_dbl_affine_val(q);   // registers stay registers; the rare call copies
+      else xyzz_dbl_affine_ni(acc, q);                              // Fp2: by reference (large by-value frames misbehave)
+    }
     else acc = Xyzz<T>::inf();
     return;
   }
@@ -182,7 +185,10 @@ B200_DEV void xyzz_add(Xyzz<T>& acc, const Xyzz<T>& q) {
   T P = U2 - U1;
   T R = S2 - S1;
   if (P.is_zero()) {
-    if (R.is_zero()) acc = xyzz_dbl_val(acc);
+    if (R.is_zero()) {
+      if constexpr (T::WORDS <= 12) acc = xyzz_dbl_val(acc);
+      else xyzz_dbl_ni(acc);
+    }
     else acc = Xyzz<T>::inf();
     return;
   }

@@ -340,30 +340,45 @@ static void FN(run_wtask)(void* arg) {
   FN(window_signed)(t->out, t->kind, t->bit_index, t->c, t->bits, t->coefs, t->points, t->n, t->f);
 }
 
-/* Signed-window bucket MSM with one task per window -- the structure of
+/* Signed-window bucket MSM, one task per (sub-MSM, window) -- the structure of
  * reference ec_multi_scalar_mul_parallel.nim:148-208 (msmImpl_vartime_parallel):
  *   numFullWindows = bits div c, numWindows = numFullWindows + 1 (the recoding needs to see an extra 0 after
- *   the MSB even when c divides bits), top window kind per :186-190, Horner with c doublings per window :198-203.
- * For c >= 9 the reference swaps Jacobian buckets for the batched-affine scheduler (:316-431) -- a CPU cache
+ *   the MSB even when c divides bits), top window kind per :186-190, Horner with c doublings per window :198-203,
+ * wrapped in the MSM-level split of :386-431 (msmAffine_vartime_parallel_split): msmParallelism = smallest power of two
+ * with (bits div c) * msmParallelism >= numThreads, points cut into balanced chunks (partitioners.nim:44), the partial
+ * results added at the end.
+ * For c >= 9 the reference swaps Jacobian buckets for the batched-affine scheduler (:316-384) -- a CPU cache
  * optimisation that yields the same group element and is not restated. */
 static void FN(msm_signed)(jac_t* r, const uint64_t* coefs, const aff_t* points, size_t n, int c, int bits,
                            const field_t* f, int nthreads) {
   int num_full = bits / c;
   int excess = bits % c, top = bits - excess;
-  jac_t* sums = (jac_t*)malloc((size_t)(num_full + 1) * sizeof(jac_t));
-  FN(wtask)* tasks = (FN(wtask)*)malloc((size_t)(num_full + 1) * sizeof(FN(wtask)));
-  for (int w = 0; w <= num_full; w++) {
-    int kind = (w == 0) ? 0 : 1;
-    int bit_index = w * c;
-    if (w == num_full) { kind = (top == 0) ? 0 : (excess == 0 ? 1 : 2); bit_index = top; }
-    FN(wtask) t = { &sums[w], kind, bit_index, c, bits, coefs, points, n, f };
-    tasks[w] = t;
+  int nwin = num_full + 1;
+  int msm_par = 1;
+  while (num_full * msm_par < nthreads && (size_t)msm_par * 2 <= n) msm_par <<= 1;
+  jac_t* sums = (jac_t*)malloc((size_t)nwin * msm_par * sizeof(jac_t));
+  FN(wtask)* tasks = (FN(wtask)*)malloc((size_t)nwin * msm_par * sizeof(FN(wtask)));
+  size_t base_chunk = n / (size_t)msm_par, cutoff = n % (size_t)msm_par;
+  for (int ch = 0; ch < msm_par; ch++) {
+    size_t start = (size_t)ch < cutoff ? (base_chunk + 1) * ch : base_chunk * ch + cutoff;
+    size_t len = (size_t)ch < cutoff ? base_chunk + 1 : base_chunk;
+    for (int w = 0; w < nwin; w++) {
+      int kind = (w == 0) ? 0 : 1;
+      int bit_index = w * c;
+      if (w == num_full) { kind = (top == 0) ? 0 : (excess == 0 ? 1 : 2); bit_index = top; }
+      FN(wtask) t = { &sums[ch * nwin + w], kind, bit_index, c, bits, coefs + start * SCALAR_LIMBS, points + start, len, f };
+      tasks[ch * nwin + w] = t;
+    }
   }
-  run_tasks(FN(run_wtask), tasks, sizeof(FN(wtask)), num_full + 1, nthreads);
-  *r = sums[num_full];
-  for (int w = num_full - 1; w >= 0; w--) {
-    for (int i = 0; i < c; i++) FN(jac_dbl)(r, r, f);
-    FN(jac_add)(r, r, &sums[w], f);
+  run_tasks(FN(run_wtask), tasks, sizeof(FN(wtask)), nwin * msm_par, nthreads);
+  FN(jac_set_inf)(r, f);
+  for (int ch = msm_par - 1; ch >= 0; ch--) {
+    jac_t acc = sums[ch * nwin + num_full];
+    for (int w = num_full - 1; w >= 0; w--) {
+      for (int i = 0; i < c; i++) FN(jac_dbl)(&acc, &acc, f);
+      FN(jac_add)(&acc, &acc, &sums[ch * nwin + w], f);
+    }
+    FN(jac_add)(r, r, &acc, f);
   }
   free(tasks);
   free(sums);

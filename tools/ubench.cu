@@ -30,9 +30,13 @@ __global__ void k_pipe(uint32_t* out, int iters, uint32_t seed) {
 #define OP(x) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(x) : "r"(a), "r"(b));
       OP(x0) OP(x1) OP(x2) OP(x3) OP(x4) OP(x5) OP(x6) OP(x7)
 #undef OP
-    } else if (MODE == 2) {  // mad.wide.u32
-#define OP(x) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x) : "r"(a), "r"(b));
-      OP(w0) OP(w1) OP(w2) OP(w3) OP(w4) OP(w5) OP(w6) OP(w7)
+    } else if (MODE == 2) {  // mad.wide.u32 with a 64-bit addend; operands differ per chain so ptxas cannot share one product
+#define OP(x, k) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x) : "r"(a + k), "r"((uint32_t)x));
+      OP(w0, 0) OP(w1, 1) OP(w2, 2) OP(w3, 3) OP(w4, 4) OP(w5, 5) OP(w6, 6) OP(w7, 7)
+#undef OP
+    } else if (MODE == 8) {  // mul.wide.u32 (no addend), results folded with xor on the ALU pipe
+#define OP(x, k) { uint64_t t; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"((uint32_t)x + k), "r"(b)); x ^= t; }
+      OP(w0, 0) OP(w1, 1) OP(w2, 2) OP(w3, 3) OP(w4, 4) OP(w5, 5) OP(w6, 6) OP(w7, 7)
 #undef OP
     } else if (MODE == 3) {  // carry chains: mad.lo.cc / madc.hi.cc pairs (4 pairs per chain, 2 chains)
       asm volatile(
@@ -323,7 +327,8 @@ int main() {
   printf("{\"device\":\"%s\",\"sms\":%d,\"clock_ghz_max\":%.3f}\n", prop.name, sms, clock_ghz);
   run_pipe<0>("mad.lo.u32", sms, clock_ghz);
   run_pipe<1>("mad.hi.u32", sms, clock_ghz);
-  run_pipe<2>("mad.wide.u32", sms, clock_ghz);
+  run_pipe<2>("mad.wide.u32 (64-bit addend, distinct operands)", sms, clock_ghz);
+  run_pipe<8>("mul.wide.u32 + xor", sms, clock_ghz);
   run_pipe<3>("mad.lo.cc+madc.hi.cc chain", sms, clock_ghz);
   run_pipe<4>("fma.rn.f64", sms, clock_ghz);
   run_pipe<5>("add.cc chain", sms, clock_ghz);
