@@ -130,13 +130,15 @@ void ctt_b200_last_stats(ctt_b200_stats* out) {
   memcpy(out, &E.stats, sizeof(Stats));
 }
 
-void ctt_b200_set_tuning(int force_c, int reduce_chunk, int sum_group) {
+void ctt_b200_set_tuning(int force_c, int reduce_chunk, int slice_len) {
+  const int sum_group = slice_len;
   Engine& E = engine();
   std::lock_guard<std::mutex> lock(E.mu);
   if (force_c > 0) E.tuning.force_c = force_c;
   if (force_c < 0) E.tuning.force_c = 0;
   if (reduce_chunk > 0) E.tuning.reduce_chunk = reduce_chunk;
-  if (sum_group > 0) E.tuning.sum_group = sum_group;
+  if (sum_group > 0) E.tuning.slice_len = sum_group;
+  if (sum_group < 0) E.tuning.slice_len = 0;
 }
 
 void ctt_b200_set_stream(void* cuda_stream) {

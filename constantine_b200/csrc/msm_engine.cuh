@@ -55,7 +55,7 @@ using Bn254G2 = CurveDesc<Bn254SnarksFp, Bn254SnarksFr, 2>;
 struct Tuning {
   int force_c = 0;            // 0 = cost model
   int reduce_chunk = 16;      // L: buckets per bucket-reduce thread
-  int sum_group = 32;         // (fixed) fan-in of the warp-butterfly row sums
+  int slice_len = 0;          // K: sorted entries per accumulate thread (0 = automatic)
 };
 
 struct Stats {               // filled per call; read back through ctt_b200_last_stats
@@ -167,8 +167,7 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   using T = typename C::T;
   using H = typename C::H;
   using HP = host::HXyzz<H>;
-  constexpr int KACC = 32;   // level-0 slice length
-  constexpr int KFIX = 8;    // fix-up slice length
+  constexpr int KFIX = 32;   // fix-up slice length
   Stats& st = E.stats;
   int launches = 0;
   if (n == 0) return HP::inf();
@@ -187,6 +186,14 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   constexpr size_t XYZZ_BYTES = 4 * T::WORDS * 4;
   st.c = c; st.num_windows = nw; st.entries = entries; st.total_buckets = nbuckets;
 
+  // level-0 slice length: about twice the mean run length (entries per bucket) so that few slices sit entirely inside
+  // one run, but never so long that the grid cannot fill the machine
+  int KACC = 32;
+  {
+    double mean_run = (double)n / (double)B;
+    while (KACC < 256 && KACC < 2.0 * mean_run && entries / (size_t)(2 * KACC) >= (size_t)4 * 148 * 256) KACC *= 2;
+    if (E.tuning.slice_len > 0) KACC = E.tuning.slice_len;
+  }
   cudaStream_t s = E.compute();
   E.keys_a.ensure(entries * 4); E.keys_b.ensure(entries * 4);
   E.vals_a.ensure(entries * 4); E.vals_b.ensure(entries * 4);
@@ -227,8 +234,8 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   if (wait_points) B200_CUDA_CHECK(cudaStreamWaitEvent(s, wait_points, 0));
   {
     dim3 block(128), grid((unsigned)((slices0 + 127) / 128));
-    k_accumulate<T, KACC><<<grid, block, 0, s>>>(keys, vals, entries, no_key, (const uint32_t*)d_points, (uint32_t*)E.buckets.ptr,
-                                                 (uint32_t*)E.part_pts[0].ptr, (uint32_t*)E.part_keys[0].ptr, slices0);
+    k_accumulate<T><<<grid, block, 0, s>>>(keys, vals, entries, no_key, (const uint32_t*)d_points, (uint32_t*)E.buckets.ptr,
+                                           (uint32_t*)E.part_pts[0].ptr, (uint32_t*)E.part_keys[0].ptr, slices0, KACC);
     launches++;
   }
   if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[3], s));

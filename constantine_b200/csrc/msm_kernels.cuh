@@ -103,29 +103,41 @@ constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 // the same warp through shared memory and added into that lane's last run before it is stored (one extra XYZZ add per
 // warp), so only heads whose predecessor lives in another warp -- or is itself a single-run continuation slice --
 // are spilled to the global partial list that k_fixup resolves.
-template <class T, int K>
-__global__ void __launch_bounds__(128) k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                                    size_t total, uint32_t no_key, const uint32_t* __restrict__ points,
-                                                    uint32_t* buckets, uint32_t* part_pts, uint32_t* part_keys, size_t num_slices) {
+#ifndef B200_ACC_MIN_BLOCKS
+#define B200_ACC_MIN_BLOCKS 2
+#endif
+template <class T>
+__global__ void __launch_bounds__(128, (T::WORDS <= 12) ? B200_ACC_MIN_BLOCKS : 1)
+k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, size_t total, uint32_t no_key,
+             const uint32_t* __restrict__ points, uint32_t* buckets, uint32_t* part_pts, uint32_t* part_keys,
+             size_t num_slices, int K) {
   __shared__ uint32_t head_smem[128 * 4 * T::WORDS];
   const unsigned lane = threadIdx.x & 31u;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = t < num_slices;
-  size_t base = t * K;
+  size_t base = t * (size_t)K;
   uint32_t prev_key = (live && t > 0) ? keys[base - 1] : KEY_NONE;
   uint32_t cur_key = KEY_NONE;
   bool head_valid = false;     // first run continues the previous slice (its sum is parked in head_smem[threadIdx.x])
   bool first_run = true;
   Xyzz<T> acc = Xyzz<T>::inf();
   if (live) {
+    // software pipeline: the (key, ref, point) of entry j+1 is fetched before the point addition of entry j is issued,
+    // so the dependent gather keys -> vals -> points overlaps ~10 field multiplications instead of stalling the warp.
+    uint32_t key_n = (base < total) ? keys[base] : no_key;
+    uint32_t v_n = 0;
+    Aff<T> p_n;
+    p_n.x = T::zero(); p_n.y = T::zero();
+    if (key_n < no_key) { v_n = vals[base]; p_n = load_affine<T>(points, v_n & 0x7FFFFFFFu); }
 #pragma unroll 1
     for (int j = 0; j < K; j++) {
-      size_t idx = base + j;
-      if (idx >= total) break;
-      uint32_t key = keys[idx];
-      if (key >= no_key) break;  // zero digits are sorted to the tail: nothing left in this slice
-      uint32_t v = vals[idx];
-      Aff<T> p = load_affine<T>(points, v & 0x7FFFFFFFu);
+      const uint32_t key = key_n;
+      if (key >= no_key) break;  // zero digits are sorted to the tail (or end of list): nothing left in this slice
+      const uint32_t v = v_n;
+      Aff<T> p = p_n;
+      const size_t nidx = base + j + 1;
+      key_n = (j + 1 < K && nidx < total) ? keys[nidx] : no_key;
+      if (key_n < no_key) { v_n = vals[nidx]; p_n = load_affine<T>(points, v_n & 0x7FFFFFFFu); }
       if (!p.is_inf()) p.y.cneg((v >> 31) != 0);
       if (key != cur_key) {
         if (cur_key != KEY_NONE) {
