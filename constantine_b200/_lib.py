@@ -17,7 +17,8 @@ class Stats(ctypes.Structure):
                 ("kernel_launches", ctypes.c_int),
                 ("ms_h2d", ctypes.c_float), ("ms_digits", ctypes.c_float), ("ms_sort", ctypes.c_float),
                 ("ms_accumulate", ctypes.c_float), ("ms_fixup", ctypes.c_float), ("ms_reduce", ctypes.c_float),
-                ("ms_d2h_tail", ctypes.c_float), ("ms_total", ctypes.c_float)]
+                ("ms_d2h_tail", ctypes.c_float), ("ms_total", ctypes.c_float),
+                ("groups", ctypes.c_int), ("slice_len", ctypes.c_int)]
 
 
 def load():
@@ -49,6 +50,8 @@ def load():
     lib.ctt_b200_last_stats.restype = None
     lib.ctt_b200_set_tuning.argtypes = [ci, ci, ci]
     lib.ctt_b200_set_tuning.restype = None
+    lib.ctt_b200_set_groups.argtypes = [ci]
+    lib.ctt_b200_set_groups.restype = None
     lib.ctt_b200_set_stream.argtypes = [vp]
     lib.ctt_b200_set_stream.restype = None
     lib.ctt_b200_sm_count.argtypes = []

@@ -141,6 +141,12 @@ void ctt_b200_set_tuning(int force_c, int reduce_chunk, int slice_len) {
   if (sum_group < 0) E.tuning.slice_len = 0;
 }
 
+void ctt_b200_set_groups(int groups) {
+  Engine& E = engine();
+  std::lock_guard<std::mutex> lock(E.mu);
+  E.tuning.groups = groups < 0 ? 0 : groups;
+}
+
 void ctt_b200_set_stream(void* cuda_stream) {
   Engine& E = engine();
   std::lock_guard<std::mutex> lock(E.mu);

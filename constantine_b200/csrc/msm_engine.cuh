@@ -56,6 +56,7 @@ struct Tuning {
   int force_c = 0;            // 0 = cost model
   int reduce_chunk = 16;      // L: buckets per bucket-reduce thread
   int slice_len = 0;          // K: sorted entries per accumulate thread (0 = automatic)
+  int groups = 0;             // window groups pipelined over side streams (0 = automatic, 1 = fully serial launch order)
 };
 
 struct Stats {               // filled per call; read back through ctt_b200_last_stats
@@ -64,6 +65,7 @@ struct Stats {               // filled per call; read back through ctt_b200_last
   unsigned long long total_buckets = 0;
   int kernel_launches = 0;              // kernels launched by the last call (ours + the radix sort's)
   float ms_h2d = 0, ms_digits = 0, ms_sort = 0, ms_accumulate = 0, ms_fixup = 0, ms_reduce = 0, ms_d2h_tail = 0, ms_total = 0;
+  int groups = 1, slice_len = 0;
 };
 
 // Window size: minimise  W*N*MADD + W*2^(c-1)*REDUCE  (same shape as the reference's bestBucketBitSize cost,
@@ -120,9 +122,12 @@ struct Engine {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaStream_t user_stream = nullptr;  // optional caller-provided compute stream (ctt_b200_set_stream)
   cudaStream_t compute() const { return user_stream ? user_stream : stream; }
+  cudaStream_t side[2] = {nullptr, nullptr};   // high-priority streams for the fix-up / reduce chains of finished window groups
   cudaEvent_t ev[10];
   cudaEvent_t ev_points_ready;
-  DeviceBuffer d_scalars, d_points, keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_pts[2], part_keys[2], red_a, red_b;
+  cudaEvent_t ev_group[64];
+  cudaEvent_t ev_side[2];
+  DeviceBuffer d_scalars, d_points, keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_pts[2], part_keys[2], red_a, red_b, bounds;
   void* h_result = nullptr;   // pinned
   size_t h_result_cap = 0;
   Tuning tuning;
@@ -144,6 +149,13 @@ struct Engine {
     sm_count = prop.multiProcessorCount;
     B200_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     B200_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    {
+      int lo = 0, hi = 0;
+      B200_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = numerically lowest = highest priority
+      for (auto& x : side) B200_CUDA_CHECK(cudaStreamCreateWithPriority(&x, cudaStreamNonBlocking, hi));
+      for (auto& x : ev_group) B200_CUDA_CHECK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+      for (auto& x : ev_side) B200_CUDA_CHECK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+    }
     for (auto& x : ev) B200_CUDA_CHECK(cudaEventCreate(&x));
     B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_points_ready, cudaEventDisableTiming));
     h_result_cap = 1 << 20;
@@ -198,10 +210,6 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   E.keys_a.ensure(entries * 4); E.keys_b.ensure(entries * 4);
   E.vals_a.ensure(entries * 4); E.vals_b.ensure(entries * 4);
   E.buckets.ensure(nbuckets * XYZZ_BYTES);
-  const size_t slices0 = (entries + KACC - 1) / KACC;
-  E.part_pts[0].ensure(slices0 * XYZZ_BYTES); E.part_keys[0].ensure(slices0 * 4);
-  const size_t slices1 = (slices0 + KFIX - 1) / KFIX;
-  E.part_pts[1].ensure(slices1 * XYZZ_BYTES); E.part_keys[1].ensure(slices1 * 4);
 
   if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[0], s));
   // 1. digits
@@ -230,32 +238,28 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   const uint32_t* vals = dv.Current();
   B200_CUDA_CHECK(cudaMemsetAsync(E.buckets.ptr, 0, nbuckets * XYZZ_BYTES, s));  // all-zero XYZZ = infinity
   if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[2], s));
-  // 3. accumulate
-  if (wait_points) B200_CUDA_CHECK(cudaStreamWaitEvent(s, wait_points, 0));
-  {
-    dim3 block(128), grid((unsigned)((slices0 + 127) / 128));
-    k_accumulate<T><<<grid, block, 0, s>>>(keys, vals, entries, no_key, (const uint32_t*)d_points, (uint32_t*)E.buckets.ptr,
-                                           (uint32_t*)E.part_pts[0].ptr, (uint32_t*)E.part_keys[0].ptr, slices0, KACC);
-    launches++;
+  // window groups: the sorted list is ordered by window, so the windows are cut into G consecutive groups whose
+  // accumulate launches run back to back on the main stream while the latency-bound fix-up / reduce chain of every
+  // finished group runs on a high-priority side stream underneath the next group's accumulate.
+  int G = E.tuning.groups > 0 ? E.tuning.groups : (entries >= ((size_t)1 << 22) ? (nw >= 12 ? 4 : (nw >= 4 ? 2 : 1)) : 1);
+  if (G > nw) G = nw;
+  if (G > 32) G = 32;
+  const int Wg = (nw + G - 1) / G;
+  G = (nw + Wg - 1) / Wg;
+  st.groups = G; st.slice_len = KACC;
+  E.bounds.ensure((size_t)(nw + 1) * 8);
+  k_window_bounds<<<1, 64, 0, s>>>(keys, entries, B, nw, (unsigned long long*)E.bounds.ptr);
+  launches++;
+  // per-group geometry (upper bounds known on the host; the exact entry ranges stay on the device)
+  std::vector<size_t> off0(G + 1, 0), off1(G + 1, 0);
+  for (int g = 0; g < G; g++) {
+    int w0 = g * Wg, w1 = (w0 + Wg < nw) ? w0 + Wg : nw;
+    size_t max_slices = ((size_t)(w1 - w0) * n + KACC - 1) / KACC;
+    off0[g + 1] = off0[g] + max_slices;
+    off1[g + 1] = off1[g] + (max_slices + KFIX - 1) / KFIX;
   }
-  if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[3], s));
-  // 4. fix-up levels
-  {
-    size_t count = slices0;
-    int cur = 0;
-    while (count > 1) {
-      size_t ns = (count + KFIX - 1) / KFIX;
-      dim3 block(128), grid((unsigned)((ns + 127) / 128));
-      k_fixup<T, KFIX><<<grid, block, 0, s>>>((const uint32_t*)E.part_keys[cur].ptr, (const uint32_t*)E.part_pts[cur].ptr, count,
-                                              (uint32_t*)E.buckets.ptr, (uint32_t*)E.part_pts[cur ^ 1].ptr, (uint32_t*)E.part_keys[cur ^ 1].ptr, ns);
-      launches++;
-      count = ns;
-      cur ^= 1;
-    }
-    // a single remaining slice never continues a previous one: its runs were all added to their buckets.
-  }
-  if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[4], s));
-  // 5. bucket reduce: chunked running sums, then warp-butterfly row sums down to <= 4 points per window
+  E.part_pts[0].ensure(off0[G] * XYZZ_BYTES); E.part_keys[0].ensure(off0[G] * 4);
+  E.part_pts[1].ensure(off1[G] * XYZZ_BYTES); E.part_keys[1].ensure(off1[G] * 4);
   constexpr bool INL = (T::WORDS <= 12);   // single-field coordinates: inline the point adds; Fp2: out-of-line (code size)
   uint32_t L = (uint32_t)E.tuning.reduce_chunk;
   if (L < 1) L = 1;
@@ -266,27 +270,84 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   while (nbits < 32 && ((uint64_t)(chunks - 1) * L >> nbits) != 0) nbits++;
   E.red_a.ensure((size_t)chunks * nw * XYZZ_BYTES);
   E.red_b.ensure((size_t)chunks * nw * XYZZ_BYTES);
-  {
-    size_t threads = (size_t)chunks * nw;
-    dim3 block(64), grid((unsigned)((threads + 63) / 64));
-    k_bucket_reduce<T, INL><<<grid, block, 0, s>>>((const uint32_t*)E.buckets.ptr, B, L, chunks, (uint32_t)nw, (uint32_t*)E.red_a.ptr,
-                                                    (uint32_t*)E.red_b.ptr);
-    k_chunk_offset<T, INL><<<grid, block, 0, s>>>((uint32_t*)E.red_a.ptr, (const uint32_t*)E.red_b.ptr, L, chunks, (uint32_t)nw, nbits);
-    launches += 2;
+  constexpr size_t XW = 4 * T::WORDS;  // 32-bit words per XYZZ point
+  uint32_t row_final = chunks;
+  bool final_in_a = true;
+  if (wait_points) B200_CUDA_CHECK(cudaStreamWaitEvent(s, wait_points, 0));
+  for (int g = 0; g < G; g++) {
+    const int w0 = g * Wg, w1 = (w0 + Wg < nw) ? w0 + Wg : nw;
+    const size_t max_slices = off0[g + 1] - off0[g];
+    // 3. accumulate (main stream)
+    {
+      dim3 block(128), grid((unsigned)((max_slices + 127) / 128));
+      k_accumulate<T><<<grid, block, 0, s>>>(keys, vals, (const unsigned long long*)E.bounds.ptr, w0, w1, no_key, (const uint32_t*)d_points,
+                                             (uint32_t*)E.buckets.ptr, (uint32_t*)E.part_pts[0].ptr + off0[g] * XW,
+                                             (uint32_t*)E.part_keys[0].ptr + off0[g], max_slices, KACC);
+      launches++;
+    }
+    cudaStream_t q = s;
+    if (G > 1) {
+      q = E.side[g & 1];
+      B200_CUDA_CHECK(cudaEventRecord(E.ev_group[g], s));
+      B200_CUDA_CHECK(cudaStreamWaitEvent(q, E.ev_group[g], 0));
+    } else if (E.collect_timing) {
+      B200_CUDA_CHECK(cudaEventRecord(E.ev[3], s));
+    }
+    // 4. fix-up levels of this group
+    {
+      size_t count = max_slices;
+      int cur = 0;
+      while (count > 1) {
+        size_t ns = (count + KFIX - 1) / KFIX;
+        dim3 block(128), grid((unsigned)((count + 127) / 128));
+        const size_t oin = cur ? off1[g] : off0[g], oout = cur ? off0[g] : off1[g];
+        k_fixup<T><<<grid, block, 0, q>>>((const uint32_t*)E.part_keys[cur].ptr + oin, (const uint32_t*)E.part_pts[cur].ptr + oin * XW, count,
+                                          (uint32_t*)E.buckets.ptr, (uint32_t*)E.part_pts[cur ^ 1].ptr + oout * XW,
+                                          (uint32_t*)E.part_keys[cur ^ 1].ptr + oout);
+        launches++;
+        count = ns;
+        cur ^= 1;
+      }
+      // the last level is a single chunk: its first entry has no predecessor, so nothing is forwarded any further
+    }
+    if (G == 1 && E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[4], s));
+    // 5. bucket reduce of this group's windows: chunked running sums, offsets, warp-butterfly row sums (<= 4 per window left)
+    {
+      const uint32_t nwg = (uint32_t)(w1 - w0);
+      size_t threads = (size_t)chunks * nwg;
+      dim3 block(64), grid((unsigned)((threads + 63) / 64));
+      uint32_t* ra = (uint32_t*)E.red_a.ptr + (size_t)w0 * chunks * XW;
+      uint32_t* rb = (uint32_t*)E.red_b.ptr + (size_t)w0 * chunks * XW;
+      k_bucket_reduce<T, INL><<<grid, block, 0, q>>>((const uint32_t*)E.buckets.ptr + (size_t)w0 * B * XW, B, L, chunks, nwg, ra, rb);
+      k_chunk_offset<T, INL><<<grid, block, 0, q>>>(ra, rb, L, chunks, nwg, nbits);
+      launches += 2;
+      uint32_t row = chunks;
+      bool in_a = true;
+      while (row > 4) {
+        uint32_t out_row = (row + 31) / 32;
+        size_t warps = (size_t)out_row * nwg;
+        dim3 blk(128), grd((unsigned)((warps * 32 + 127) / 128));
+        // rows of a level live at window-major offsets computed with that level's row length
+        const uint32_t* in = (const uint32_t*)(in_a ? E.red_a.ptr : E.red_b.ptr) + (size_t)w0 * row * XW;
+        uint32_t* out = (uint32_t*)(in_a ? E.red_b.ptr : E.red_a.ptr) + (size_t)w0 * out_row * XW;
+        k_row_sum_warp<T, INL><<<grd, blk, 0, q>>>(in, row, out_row, nwg, out);
+        launches++;
+        row = out_row;
+        in_a = !in_a;
+      }
+      row_final = row;
+      final_in_a = in_a;
+    }
+    if (G > 1) B200_CUDA_CHECK(cudaEventRecord(E.ev_side[g & 1], q));
   }
-  uint32_t row = chunks;
-  DeviceBuffer* src = &E.red_a;
-  DeviceBuffer* dst = &E.red_b;
-  while (row > 4) {
-    uint32_t out_row = (row + 31) / 32;
-    dst->ensure((size_t)out_row * nw * XYZZ_BYTES);
-    size_t warps = (size_t)out_row * nw;
-    dim3 block(128), grid((unsigned)((warps * 32 + 127) / 128));
-    k_row_sum_warp<T, INL><<<grid, block, 0, s>>>((const uint32_t*)src->ptr, row, out_row, (uint32_t)nw, (uint32_t*)dst->ptr);
-    launches++;
-    row = out_row;
-    DeviceBuffer* tmp = src; src = dst; dst = tmp;
+  if (G > 1) {
+    if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[3], s));   // end of the last accumulate
+    B200_CUDA_CHECK(cudaStreamWaitEvent(s, E.ev_side[0], 0));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(s, E.ev_side[1], 0));
+    if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[4], s));
   }
+  const uint32_t row = row_final;
+  DeviceBuffer* src = final_in_a ? &E.red_a : &E.red_b;
   if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[5], s));
   // 6. per-window partial sums (<= 4 each) -> host; finish the sums and run the Horner tail there
   const size_t out_bytes = (size_t)nw * row * XYZZ_BYTES;

@@ -108,14 +108,17 @@ constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 #endif
 template <class T>
 __global__ void __launch_bounds__(128, (T::WORDS <= 12) ? B200_ACC_MIN_BLOCKS : 1)
-k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, size_t total, uint32_t no_key,
-             const uint32_t* __restrict__ points, uint32_t* buckets, uint32_t* part_pts, uint32_t* part_keys,
-             size_t num_slices, int K) {
+k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const unsigned long long* __restrict__ bounds,
+             int w0, int w1, uint32_t no_key, const uint32_t* __restrict__ points, uint32_t* buckets, uint32_t* part_pts,
+             uint32_t* part_keys, size_t max_slices, int K) {
+  // entries of windows [w0, w1) occupy sorted positions [begin, total); slices are counted from `begin`
+  const size_t begin = (size_t)bounds[w0], total = (size_t)bounds[w1];
+  const size_t num_slices = (total - begin + (size_t)K - 1) / (size_t)K;
   __shared__ uint32_t head_smem[128 * 4 * T::WORDS];
   const unsigned lane = threadIdx.x & 31u;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = t < num_slices;
-  size_t base = t * (size_t)K;
+  size_t base = begin + t * (size_t)K;
   uint32_t prev_key = (live && t > 0) ? keys[base - 1] : KEY_NONE;
   uint32_t cur_key = KEY_NONE;
   bool head_valid = false;     // first run continues the previous slice (its sum is parked in head_smem[threadIdx.x])
@@ -167,8 +170,8 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
     }
     store_xyzz(buckets, (size_t)cur_key, acc);
   }
-  if (live) {
-    if (head_valid && !prev_absorbs) {
+  if (t < max_slices) {   // every slot of the group's partial list is written (slots past the last slice are holes)
+    if (live && head_valid && !prev_absorbs) {
       Xyzz<T> h = load_xyzz<T>(head_smem, threadIdx.x);
       store_xyzz(part_pts, t, h);
       part_keys[t] = prev_key;
@@ -178,41 +181,51 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
   }
 }
 
-// Fix-up level: input = list of (key, XYZZ) partials in slice order (KEY_NONE entries are holes).  Equal keys are
-// contiguous.  Same slicing; a run continuing from the previous slice is forwarded to the next level, every other
-// run is added into its bucket (exactly one thread per key and level does so).
-template <class T, int K>
+// bounds[w] = first sorted position whose key is >= w * B  (w = 0..num_windows; keys of zero digits sort last)
+static __global__ void k_window_bounds(const uint32_t* __restrict__ keys, size_t total, uint32_t B, int num_windows, unsigned long long* bounds) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w > num_windows) return;
+  const uint64_t target = (uint64_t)w * B;
+  size_t lo = 0, hi = total;
+  while (lo < hi) {
+    size_t mid = lo + (hi - lo) / 2;
+    if ((uint64_t)keys[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  bounds[w] = (unsigned long long)lo;
+}
+
+// Fix-up level: input = list of (key, XYZZ) partials in slice order (KEY_NONE entries are holes); equal keys are
+// contiguous. ONE THREAD PER ENTRY, the list is cut into chunks of R = 32 entries (= one warp): the first entry of every
+// run inside a chunk sums its run (usually a single entry, so all additions of a level run side by side). A run that
+// starts at a chunk boundary and continues the previous chunk is forwarded to the next level (slot = chunk index);
+// every other run is added into its bucket -- exactly one thread per key and level does so.
+template <class T>
 __global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ in_keys, const uint32_t* in_pts, size_t count,
-                                               uint32_t* buckets, uint32_t* out_pts, uint32_t* out_keys, size_t num_slices) {
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= num_slices) return;
-  size_t base = t * K;
-  uint32_t prev_key = (t > 0) ? in_keys[base - 1] : KEY_NONE;
-  uint32_t cur_key = KEY_NONE;
-  bool wrote_partial = false;
-  Xyzz<T> acc = Xyzz<T>::inf();
+                                               uint32_t* buckets, uint32_t* out_pts, uint32_t* out_keys) {
+  constexpr int R = 32;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t key = in_keys[i];
+  const bool chunk_first = (i % R) == 0;
+  const uint32_t prev = (i > 0) ? in_keys[i - 1] : KEY_NONE;
+  const bool continues = key != KEY_NONE && prev == key;       // same run as the previous entry
+  if (chunk_first && !continues) out_keys[i / R] = KEY_NONE;    // this chunk forwards nothing
+  if (key == KEY_NONE) return;
+  if (continues && !chunk_first) return;                        // interior of a run: its head does the work
+  Xyzz<T> acc = load_xyzz<T>(in_pts, i);
 #pragma unroll 1
-  for (int j = 0; j < K; j++) {
-    size_t idx = base + j;
-    if (idx >= count) break;
-    uint32_t key = in_keys[idx];
-    if (key != cur_key) {
-      if (cur_key != KEY_NONE) {
-        if (cur_key == prev_key) { store_xyzz(out_pts, t, acc); out_keys[t] = cur_key; wrote_partial = true; }
-        else { Xyzz<T> b = load_xyzz<T>(buckets, (size_t)cur_key); xyzz_add_ni(b, acc); store_xyzz(buckets, (size_t)cur_key, b); }
-      }
-      cur_key = key;
-      if (key != KEY_NONE) acc = load_xyzz<T>(in_pts, idx);
-    } else if (key != KEY_NONE) {
-      Xyzz<T> q = load_xyzz<T>(in_pts, idx);
-      xyzz_add_ni(acc, q);
-    }
+  for (size_t j = i + 1; j < count && (j % R) != 0 && in_keys[j] == key; j++) {
+    Xyzz<T> q = load_xyzz<T>(in_pts, j);
+    xyzz_add_ni(acc, q);
   }
-  if (cur_key != KEY_NONE) {
-    if (cur_key == prev_key) { store_xyzz(out_pts, t, acc); out_keys[t] = cur_key; wrote_partial = true; }
-    else { Xyzz<T> b = load_xyzz<T>(buckets, (size_t)cur_key); xyzz_add_ni(b, acc); store_xyzz(buckets, (size_t)cur_key, b); }
+  if (continues) {  // chunk_first && continues: hand the partial sum to the next level
+    store_xyzz(out_pts, i / R, acc);
+    out_keys[i / R] = key;
+  } else {
+    Xyzz<T> b = load_xyzz<T>(buckets, (size_t)key);
+    xyzz_add_ni(b, acc);
+    store_xyzz(buckets, (size_t)key, b);
   }
-  if (!wrote_partial) out_keys[t] = KEY_NONE;
 }
 
 // ------------------------------------------------------------------------------------------- bucket reduction
