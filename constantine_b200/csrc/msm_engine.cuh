@@ -241,14 +241,16 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   // window groups: the sorted list is ordered by window, so the windows are cut into G consecutive groups whose
   // accumulate launches run back to back on the main stream while the latency-bound fix-up / reduce chain of every
   // finished group runs on a high-priority side stream underneath the next group's accumulate.
-  int G = E.tuning.groups > 0 ? E.tuning.groups : (entries >= ((size_t)1 << 22) ? (nw >= 12 ? 4 : (nw >= 4 ? 2 : 1)) : 1);
+  // Measured on B200 at N = 2^20 (profiles/README.md): splitting the accumulate into per-group launches costs more in
+  // partial waves than the overlap wins back, so the default is ONE group; the knob stays for experiments.
+  int G = E.tuning.groups > 0 ? E.tuning.groups : 1;
   if (G > nw) G = nw;
   if (G > 32) G = 32;
   const int Wg = (nw + G - 1) / G;
   G = (nw + Wg - 1) / Wg;
   st.groups = G; st.slice_len = KACC;
   E.bounds.ensure((size_t)(nw + 1) * 8);
-  k_window_bounds<<<1, 64, 0, s>>>(keys, entries, B, nw, (unsigned long long*)E.bounds.ptr);
+  k_window_bounds<<<(unsigned)((nw + 1 + 63) / 64), 64, 0, s>>>(keys, entries, B, nw, (unsigned long long*)E.bounds.ptr);
   launches++;
   // per-group geometry (upper bounds known on the host; the exact entry ranges stay on the device)
   std::vector<size_t> off0(G + 1, 0), off1(G + 1, 0);
