@@ -267,3 +267,31 @@ def scalar_to_bytes(k: int, curve: CurveParams, fr_mont=False) -> bytes:
     if fr_mont:
         return fe_to_bytes(k % curve.fr.modulus, curve.fr, mont=True)
     return k.to_bytes(curve.fr.nbytes, "little")
+
+
+# ---------------------------------------------------------------- BLS12-381 G1 compressed encoding (ZCash / IETF format)
+# used by the reference's KZG known-answer vectors (reference constantine/serialization/codecs_bls12_381.nim,
+# tests/protocol_ethereum_eip4844_deneb_kzg/): 48 bytes big-endian x, flag bits in the top byte:
+#   0x80 compressed, 0x40 infinity, 0x20 set iff y is the lexicographically larger root (y > (p-1)/2).
+def bls12_381_g1_decompress(b: bytes, curve: CurveParams):
+    assert len(b) == 48 and (b[0] & 0x80)
+    if b[0] & 0x40:
+        return None
+    p = curve.fp.modulus
+    x = int.from_bytes(bytes([b[0] & 0x1F]) + b[1:], "big")
+    y2 = (x * x * x + curve.b[0]) % p
+    y = pow(y2, (p + 1) // 4, p)          # p = 3 mod 4
+    assert (y * y) % p == y2, "not on curve"
+    if bool(b[0] & 0x20) != (y > (p - 1) // 2):
+        y = p - y
+    return ((x,), (y,))
+
+
+def bls12_381_g1_compress(P, curve: CurveParams) -> bytes:
+    if P is None:
+        return bytes([0xC0]) + bytes(47)
+    p = curve.fp.modulus
+    x, y = P[0][0], P[1][0]
+    raw = bytearray(x.to_bytes(48, "big"))
+    raw[0] |= 0x80 | (0x20 if y > (p - 1) // 2 else 0)
+    return bytes(raw)
