@@ -171,6 +171,24 @@ def test_every_window_size_same_point(M, lib, rng):
         assert pyref.jac_bytes_to_affine(M.sum_partials(cv, parts, 3), cv) == want, ("window ranges", c)
 
 
+def test_host_entry_raw_partial_output(M, lib, oracle_lib, rng):
+    """ctt_b200_msm_host with CTT_B200_OUT_XYZZ (what a rank contributes to the multi-GPU all_gather): two half-MSMs
+    combined by ctt_b200_sum_partials equal the whole MSM."""
+    cv = CURVES["pallas_ec"]
+    _, pool = point_pool(cv)
+    n = 2000
+    pts = [pool[rng.randrange(len(pool))] for _ in range(n)]
+    ks = [rng.getrandbits(255) for _ in range(n)]
+    cb, pb = pack(cv, ks, pts)
+    want = pyref.jac_bytes_to_affine(oracle_lib.msm(cv, cb, pb, n), cv)
+    parts = b""
+    for lo, hi in ((0, 900), (900, n)):
+        r = ctypes.create_string_buffer(4 * cv.coord_bytes)
+        assert lib.ctt_b200_msm_host(cv.curve_id, M.OUT_XYZZ, r, cb[32 * lo:32 * hi], pb[cv.aff_bytes * lo:cv.aff_bytes * hi], hi - lo, 0) == 0
+        parts += r.raw
+    assert pyref.jac_bytes_to_affine(M.sum_partials(cv, parts, 2), cv) == want
+
+
 def test_cached_bases(M, oracle_lib, rng):
     """device-resident bases (the C face of the reference ZAL's base caching)"""
     cv = CURVES["bn254_snarks_g1"]
