@@ -161,17 +161,40 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
   if (last_is_head) { store_xyzz(head_smem, threadIdx.x, acc); head_valid = true; }
   const bool absorber = has_run && !last_is_head;                        // owns the bucket of its last run
   __syncwarp();
-  const bool prev_absorbs = __shfl_up_sync(0xFFFFFFFFu, absorber ? 1 : 0, 1) != 0 && lane > 0;
-  const bool next_has_head = __shfl_down_sync(0xFFFFFFFFu, head_valid ? 1 : 0, 1) != 0 && lane < 31;
-  if (absorber) {
-    if (next_has_head) {
-      Xyzz<T> h = load_xyzz<T>(head_smem, threadIdx.x + 1);
+  // Which heads can be taken over inside the warp?  Lane a (an absorber) takes the heads of lanes a+1 .. a+m where
+  // lanes a+1 .. a+m-1 are single-run continuation slices ("through" lanes, same key as a's last run) and lane a+m is
+  // the first lane after them that has a head. A head whose chain of through lanes reaches back to lane 0 without
+  // meeting an absorber goes to the global partial list instead.
+  const unsigned through_mask = __ballot_sync(0xFFFFFFFFu, last_is_head);
+  const unsigned head_mask = __ballot_sync(0xFFFFFFFFu, head_valid);
+  const unsigned absorber_mask = __ballot_sync(0xFFFFFFFFu, absorber);
+  int take = 0;   // number of consecutive heads this lane adds to its last run
+  if (absorber && lane < 31) {
+    const unsigned above_through = through_mask >> (lane + 1);
+    const int r = __ffs(~above_through) - 1;           // consecutive through lanes right after this lane (<= 31 - lane)
+    take = r;
+    const int nxt = (int)lane + 1 + r;                  // first non-through lane after them
+    if (nxt < 32 && ((head_mask >> nxt) & 1u)) take = r + 1;
+  }
+  bool head_absorbed = false;
+  if (head_valid && lane > 0) {
+    const unsigned below_not_through = ~through_mask & ((1u << lane) - 1u);
+    if (below_not_through) {
+      const int a = 31 - __clz(below_not_through);      // nearest non-through lane below
+      head_absorbed = ((absorber_mask >> a) & 1u) != 0;
+    }
+  }
+  const int max_take = __reduce_max_sync(0xFFFFFFFFu, take);
+#pragma unroll 1
+  for (int sidx = 1; sidx <= max_take; sidx++) {
+    if (sidx <= take) {
+      Xyzz<T> h = load_xyzz<T>(head_smem, threadIdx.x + sidx);
       xyzz_add(acc, h);
     }
-    store_xyzz(buckets, (size_t)cur_key, acc);
   }
+  if (absorber) store_xyzz(buckets, (size_t)cur_key, acc);
   if (t < max_slices) {   // every slot of the group's partial list is written (slots past the last slice are holes)
-    if (live && head_valid && !prev_absorbs) {
+    if (live && head_valid && !head_absorbed) {
       Xyzz<T> h = load_xyzz<T>(head_smem, threadIdx.x);
       store_xyzz(part_pts, t, h);
       part_keys[t] = prev_key;
