@@ -41,6 +41,9 @@ ALGO_BYTES_PER_TERM = 128                # 32 B scalar + 96 B affine point
 # => 148 SMs x 31.65 x 1.965 GHz = 9.2e12 MACs/s.  (A carry-free reduced-radix multiplier was prototyped and is slower:
 # profiles/ubench_r1b.jsonl.)
 INT_MAC_PEAK_PER_S = 9.205e12
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_accumulate launch at N = 2^20, c = 16 from the committed
+# `ncu --set full` capture (profiles/ncu_k_accumulate_r1.txt): 1.413 GB + 0.098 GB.
+NCU_TRAFFIC_BYTES_N20 = 1.511e9
 
 
 def dist_env():
@@ -362,7 +365,10 @@ def main():
         "ms_per_step_serial_launch_order": ms_serial, "window_groups": st["groups"], "slice_len": st["slice_len"],
         "roofline": {"bound": "int32-mad (neither hbm nor tensor: see roofline_hbm)", "kernel": "k_accumulate",
                      "achieved": achieved / 1e12, "peak": INT_MAC_PEAK_PER_S / 1e12, "unit": "TMAC/s (32x32->64)",
-                     "frac": achieved / INT_MAC_PEAK_PER_S, "traffic": None,
+                     "frac": achieved / INT_MAC_PEAK_PER_S,
+                     "traffic": (NCU_TRAFFIC_BYTES_N20 if (world == 1 and args.logn == 20 and st["c"] == 16) else None),
+                     "traffic_note": "DRAM bytes of one k_accumulate launch from profiles/ncu_k_accumulate_r1.txt; algorithmic gather = entries x 96 B = 1.61e9 B",
+                     "fmaheavy_pipe_busy_ncu": 0.82,
                      "peak_source": "measured 32x32->64 MAC rate (IMAD.WIDE.U32.X chains, 31.65/clk/SM x 148 SM x 1.965 GHz), tools/ubench.cu -> profiles/ubench_r1.jsonl",
                      "algorithmic_work": f"{madds} bucket point-adds x {INT_MACS_PER_POINT_ADD} MACs per launch, {acc_ms:.3f} ms"},
         "roofline_hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,

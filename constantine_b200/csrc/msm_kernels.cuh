@@ -161,36 +161,16 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
   if (last_is_head) { store_xyzz(head_smem, threadIdx.x, acc); head_valid = true; }
   const bool absorber = has_run && !last_is_head;                        // owns the bucket of its last run
   __syncwarp();
-  // Which heads can be taken over inside the warp?  Lane a (an absorber) takes the heads of lanes a+1 .. a+m where
-  // lanes a+1 .. a+m-1 are single-run continuation slices ("through" lanes, same key as a's last run) and lane a+m is
-  // the first lane after them that has a head. A head whose chain of through lanes reaches back to lane 0 without
-  // meeting an absorber goes to the global partial list instead.
-  const unsigned through_mask = __ballot_sync(0xFFFFFFFFu, last_is_head);
-  const unsigned head_mask = __ballot_sync(0xFFFFFFFFu, head_valid);
-  const unsigned absorber_mask = __ballot_sync(0xFFFFFFFFu, absorber);
-  int take = 0;   // number of consecutive heads this lane adds to its last run
-  if (absorber && lane < 31) {
-    const unsigned above_through = through_mask >> (lane + 1);
-    const int r = __ffs(~above_through) - 1;           // consecutive through lanes right after this lane (<= 31 - lane)
-    take = r;
-    const int nxt = (int)lane + 1 + r;                  // first non-through lane after them
-    if (nxt < 32 && ((head_mask >> nxt) & 1u)) take = r + 1;
-  }
-  bool head_absorbed = false;
-  if (head_valid && lane > 0) {
-    const unsigned below_not_through = ~through_mask & ((1u << lane) - 1u);
-    if (below_not_through) {
-      const int a = 31 - __clz(below_not_through);      // nearest non-through lane below
-      head_absorbed = ((absorber_mask >> a) & 1u) != 0;
-    }
-  }
-  const int max_take = __reduce_max_sync(0xFFFFFFFFu, take);
-#pragma unroll 1
-  for (int sidx = 1; sidx <= max_take; sidx++) {
-    if (sidx <= take) {
-      Xyzz<T> h = load_xyzz<T>(head_smem, threadIdx.x + sidx);
-      xyzz_add(acc, h);
-    }
+  // A lane that owns the bucket of its last run takes over the head of the next lane (same key by construction);
+  // heads whose predecessor lane cannot do that (lane 0, or a predecessor that is itself a single-run continuation
+  // slice) go to the global partial list. Longer chains are cheaper to resolve there (warp butterflies in k_fixup)
+  // than by serial additions here.
+  const bool prev_absorbs = __shfl_up_sync(0xFFFFFFFFu, absorber ? 1 : 0, 1) != 0 && lane > 0;
+  const bool next_has_head = __shfl_down_sync(0xFFFFFFFFu, head_valid ? 1 : 0, 1) != 0 && lane < 31;
+  const bool head_absorbed = head_valid && prev_absorbs;
+  if (absorber && next_has_head) {
+    Xyzz<T> h = load_xyzz<T>(head_smem, threadIdx.x + 1);
+    xyzz_add(acc, h);
   }
   if (absorber) store_xyzz(buckets, (size_t)cur_key, acc);
   if (t < max_slices) {   // every slot of the group's partial list is written (slots past the last slice are holes)
@@ -218,32 +198,45 @@ static __global__ void k_window_bounds(const uint32_t* __restrict__ keys, size_t
 }
 
 // Fix-up level: input = list of (key, XYZZ) partials in slice order (KEY_NONE entries are holes); equal keys are
-// contiguous. ONE THREAD PER ENTRY, the list is cut into chunks of R = 32 entries (= one warp): the first entry of every
-// run inside a chunk sums its run (usually a single entry, so all additions of a level run side by side). A run that
-// starts at a chunk boundary and continues the previous chunk is forwarded to the next level (slot = chunk index);
-// every other run is added into its bucket -- exactly one thread per key and level does so.
+// contiguous. One thread per entry, one warp per chunk of 32 entries. Runs of equal keys inside a chunk are summed with a
+// segmented butterfly over shuffles (5 dependent additions for a chunk-long run instead of 31; steps in which no lane has
+// a partner are skipped, so sparse lists cost nothing). The sum of a run that starts at the chunk boundary and continues
+// the previous chunk is forwarded to the next level (slot = chunk index); every other run is added into its bucket --
+// exactly one thread per key and level does so.
 template <class T>
 __global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ in_keys, const uint32_t* in_pts, size_t count,
                                                uint32_t* buckets, uint32_t* out_pts, uint32_t* out_keys) {
-  constexpr int R = 32;
+  const unsigned lane = threadIdx.x & 31u;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  const uint32_t key = in_keys[i];
-  const bool chunk_first = (i % R) == 0;
-  const uint32_t prev = (i > 0) ? in_keys[i - 1] : KEY_NONE;
-  const bool continues = key != KEY_NONE && prev == key;       // same run as the previous entry
-  if (chunk_first && !continues) out_keys[i / R] = KEY_NONE;    // this chunk forwards nothing
-  if (key == KEY_NONE) return;
-  if (continues && !chunk_first) return;                        // interior of a run: its head does the work
-  Xyzz<T> acc = load_xyzz<T>(in_pts, i);
+  const bool in_range = i < count;
+  const uint32_t key = in_range ? in_keys[i] : KEY_NONE;
+  const uint32_t prev = (in_range && i > 0) ? in_keys[i - 1] : KEY_NONE;
+  const bool valid = key != KEY_NONE;
+  const bool continues = valid && prev == key;                 // same run as the previous entry
+  Xyzz<T> acc = valid ? load_xyzz<T>(in_pts, i) : Xyzz<T>::inf();
 #pragma unroll 1
-  for (size_t j = i + 1; j < count && (j % R) != 0 && in_keys[j] == key; j++) {
-    Xyzz<T> q = load_xyzz<T>(in_pts, j);
-    xyzz_add_ni(acc, q);
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t other_key = __shfl_down_sync(0xFFFFFFFFu, key, d);
+    const bool take = valid && (lane + d < 32u) && other_key == key;
+    if (__any_sync(0xFFFFFFFFu, take)) {
+      Xyzz<T> other;
+#pragma unroll
+      for (int k = 0; k < T::WORDS; k++) {
+        other.x.set_word(k, __shfl_down_sync(0xFFFFFFFFu, acc.x.word(k), d));
+        other.y.set_word(k, __shfl_down_sync(0xFFFFFFFFu, acc.y.word(k), d));
+        other.zz.set_word(k, __shfl_down_sync(0xFFFFFFFFu, acc.zz.word(k), d));
+        other.zzz.set_word(k, __shfl_down_sync(0xFFFFFFFFu, acc.zzz.word(k), d));
+      }
+      if (take) xyzz_add_ni(acc, other);
+    }
   }
-  if (continues) {  // chunk_first && continues: hand the partial sum to the next level
-    store_xyzz(out_pts, i / R, acc);
-    out_keys[i / R] = key;
+  if (!in_range) return;
+  if (lane == 0 && !continues) out_keys[i / 32] = KEY_NONE;    // this chunk forwards nothing
+  if (!valid) return;
+  if (continues && lane != 0) return;                           // interior of a run: its first lane holds the sum
+  if (continues) {                                              // lane 0 continuing the previous chunk's run
+    store_xyzz(out_pts, i / 32, acc);
+    out_keys[i / 32] = key;
   } else {
     Xyzz<T> b = load_xyzz<T>(buckets, (size_t)key);
     xyzz_add_ni(b, acc);
