@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(64) k_bucket_reduce(const uint32_t* buckets, u
   store_xyzz(out_run, g, run);
 }
 
-// acc[g] += (t*L) * run[g]   -- double-and-add over `nbits` bits (uniform trip count; lanes whose bit is clear idle)
+// acc[g] += (t*L) * run[g]   -- 2-bit fixed-window scalar multiplication over `nbits` bits (uniform trip count):
+// table {run, 2 run, 3 run}, then per digit two doublings and one table addition (skipped by lanes whose digit is 0).
 template <class T, bool INL>
 __global__ void __launch_bounds__(64) k_chunk_offset(uint32_t* acc_io, const uint32_t* run_in, uint32_t L, uint32_t chunks_per_window,
                                                      uint32_t num_windows, int nbits) {
@@ -289,11 +290,22 @@ __global__ void __launch_bounds__(64) k_chunk_offset(uint32_t* acc_io, const uin
   const uint32_t off = (uint32_t)(g % chunks_per_window) * L;
   if (off == 0) return;
   Xyzz<T> run = load_xyzz<T>(run_in, g);
+  if (run.is_inf()) return;
+  Xyzz<T> run2 = run;
+  pdbl<T, INL>(run2);
+  Xyzz<T> run3 = run2;
+  padd<T, INL>(run3, run);
   Xyzz<T> m = Xyzz<T>::inf();
+  const int digits = (nbits + 1) / 2;
 #pragma unroll 1
-  for (int bit = nbits - 1; bit >= 0; bit--) {
+  for (int d = digits - 1; d >= 0; d--) {
     pdbl<T, INL>(m);
-    if ((off >> bit) & 1u) padd<T, INL>(m, run);
+    pdbl<T, INL>(m);
+    const uint32_t w = (off >> (2 * d)) & 3u;
+    if (w) {
+      Xyzz<T> sel = (w == 1u) ? run : ((w == 2u) ? run2 : run3);
+      padd<T, INL>(m, sel);
+    }
   }
   Xyzz<T> acc = load_xyzz<T>(acc_io, g);
   padd<T, false>(acc, m);
