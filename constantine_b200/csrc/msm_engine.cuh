@@ -261,7 +261,10 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   }
   E.part_pts[0].ensure(off0[G] * XYZZ_BYTES); E.part_keys[0].ensure(off0[G] * 4);
   E.part_pts[1].ensure(off1[G] * XYZZ_BYTES); E.part_keys[1].ensure(off1[G] * 4);
-  constexpr bool INL = (T::WORDS <= 12);   // single-field coordinates: inline the point adds; Fp2: out-of-line (code size)
+#ifndef B200_INLINE_MAX_WORDS
+#define B200_INLINE_MAX_WORDS 12
+#endif
+  constexpr bool INL = (T::WORDS <= B200_INLINE_MAX_WORDS);   // single-field coordinates: inline the point adds; Fp2: out-of-line (code size)
   uint32_t L = (uint32_t)E.tuning.reduce_chunk;
   if (L < 1) L = 1;
   uint32_t chunks = (B + L - 1) / L;
