@@ -44,6 +44,8 @@ def load():
     lib.ctt_b200_bases_upload.restype = vp
     lib.ctt_b200_bases_free.argtypes = [vp]
     lib.ctt_b200_bases_free.restype = None
+    lib.ctt_b200_bases_precompute.argtypes = [vp, ci]
+    lib.ctt_b200_bases_precompute.restype = ci
     lib.ctt_b200_msm_cached_bases.argtypes = [vp, ci, vp, vp, sz, ci]
     lib.ctt_b200_msm_cached_bases.restype = ci
     lib.ctt_b200_last_stats.argtypes = [ctypes.POINTER(Stats)]

@@ -16,6 +16,8 @@ struct Bases {
   int curve_id;
   size_t len;
   void* d_points;
+  void* d_table = nullptr;   // [table_W][len] precomputed window multiples (optional)
+  int table_c = 0, table_W = 0;
 };
 }  // namespace b200
 
@@ -40,7 +42,7 @@ int ctt_cpu_get_num_threads_os(void) { return (int)std::thread::hardware_concurr
 int ctt_b200_msm_device(int curve_id, int out_kind, void* r, const void* d_coefs, const void* d_points, size_t len,
                         int fr_mont, int force_c, int win_begin, int win_end) {
   switch (curve_id) {
-#define X(ID, DESC) case ID: msm_dev_ptrs<DESC>(r, d_coefs, d_points, len, fr_mont != 0, out_kind, force_c, win_begin, win_end); return 0;
+#define X(ID, DESC) case ID: msm_dev_ptrs<DESC>(r, d_coefs, d_points, len, fr_mont != 0, out_kind, force_c, win_begin, win_end, 0); return 0;
     B200_FOR_EACH_CURVE(X)
 #undef X
   }
@@ -106,7 +108,32 @@ void ctt_b200_bases_free(ctt_b200_bases* bases) {
   Bases* b = reinterpret_cast<Bases*>(bases);
   if (!b) return;
   cudaFree(b->d_points);
+  if (b->d_table) cudaFree(b->d_table);
   delete b;
+}
+
+int ctt_b200_bases_precompute(ctt_b200_bases* bases, int c) {
+  Bases* b = reinterpret_cast<Bases*>(bases);
+  if (!b || b->len == 0) return -1;
+  if (b->d_table) { cudaFree(b->d_table); b->d_table = nullptr; }
+  int bits = 0;
+  switch (b->curve_id) {
+#define X(ID, DESC) case ID: bits = DESC::SCALAR_BITS; break;
+    B200_FOR_EACH_CURVE(X)
+#undef X
+    default: return -1;
+  }
+  if (c <= 0) c = choose_window_table(b->len, bits);
+  if (c < 2) c = 2;
+  if (c > 20) c = 20;
+  if ((size_t)(bits / c + 1) * b->len >= (1ull << 31)) return -2;
+  switch (b->curve_id) {
+#define X(ID, DESC) case ID: b->d_table = run_precompute_table<DESC>(b->d_points, b->len, c, &b->table_W); break;
+    B200_FOR_EACH_CURVE(X)
+#undef X
+  }
+  b->table_c = c;
+  return c;
 }
 
 int ctt_b200_msm_cached_bases(const ctt_b200_bases* bases, int out_kind, void* r, const void* coefs, size_t len, int fr_mont) {
@@ -119,6 +146,14 @@ int ctt_b200_msm_cached_bases(const ctt_b200_bases* bases, int out_kind, void* r
     E.d_scalars.ensure(len * 32 + 16);
     B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, len * 32, cudaMemcpyHostToDevice, E.compute()));
     B200_CUDA_CHECK(cudaStreamSynchronize(E.compute()));
+  }
+  if (b->d_table) {
+    switch (b->curve_id) {
+#define X(ID, DESC) case ID: msm_dev_ptrs<DESC>(r, E.d_scalars.ptr, b->d_table, len, fr_mont != 0, out_kind, b->table_c, 0, -1, b->len); return 0;
+      B200_FOR_EACH_CURVE(X)
+#undef X
+    }
+    return -1;
   }
   return ctt_b200_msm_device(b->curve_id, out_kind, r, E.d_scalars.ptr, b->d_points, len, fr_mont, 0, 0, -1);
 }

@@ -85,6 +85,19 @@ inline int choose_window(size_t n, int bits, int num_devices_windows = 1) {
   return best_c;
 }
 
+// Window size when every window shares one bucket set (precomputed tables): W*N accumulated entries, 2^(c-1) buckets once.
+inline int choose_window_table(size_t n, int bits) {
+  double best = 1e300;
+  int best_c = 2;
+  for (int c = 2; c <= 20; c++) {
+    int W = bits / c + 1;
+    double cost = (double)W * (double)n * 10.0 + (double)(1u << (c - 1)) * 80.0;
+    if ((double)W * (double)n >= 2147483648.0) continue;
+    if (cost < best) { best = cost; best_c = c; }
+  }
+  return best_c;
+}
+
 inline DigitPlan make_plan(int bits, int c, int win_begin = 0, int win_end = -1) {
   DigitPlan p;
   p.bits = bits; p.c = c;
@@ -172,9 +185,13 @@ inline Engine& engine() {
 // d_scalars: n x 32 B, d_points: n affine points (ABI layout, Montgomery residues). Produces the window sums in pinned
 // host memory and runs the host tail. Window range [win_begin, win_end) lets several devices split one MSM by windows;
 // the returned point is then  sum_{w in range} 2^(c*w) * S_w.
+// Table mode (table_stride > 0): d_points is a [W][table_stride] array holding 2^(c*w) * P_i in affine form (built by
+// precompute_table below for cached bases). Every window then drops its points into ONE shared set of 2^(c-1) buckets,
+// so the bucket reduction runs once instead of W times and the Horner tail disappears.
 template <class C>
 host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const void* d_points, size_t n, bool fr_mont,
-                                      int force_c, int win_begin, int win_end, cudaEvent_t wait_points = nullptr) {
+                                      int force_c, int win_begin, int win_end, cudaEvent_t wait_points = nullptr,
+                                      size_t table_stride = 0) {
   using T = typename C::T;
   using H = typename C::H;
   using HP = host::HXyzz<H>;
@@ -188,20 +205,23 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   if (c < 2) c = 2;
   if (c > 20) c = 20;
   DigitPlan plan = make_plan(C::SCALAR_BITS, c, win_begin, win_end);
-  const int nw = plan.win_end - plan.win_begin;
-  if (nw <= 0) return HP::inf();
-  const size_t entries = (size_t)nw * n;
+  const int nwd = plan.win_end - plan.win_begin;          // digit windows handled by this call
+  if (nwd <= 0) return HP::inf();
+  const bool table_mode = table_stride > 0;
+  const int nw = table_mode ? 1 : nwd;                    // bucket sets ("logical windows")
+  const size_t entries = (size_t)nwd * n;
+  if (table_mode && (size_t)nwd * table_stride >= (1ull << 31)) { fprintf(stderr, "[ctt_b200_msm] FATAL: table too large\n"); abort(); }
   const uint32_t B = plan.buckets_per_window;
   const size_t nbuckets = (size_t)nw * B;
   const uint32_t no_key = (uint32_t)nbuckets;
   constexpr size_t XYZZ_BYTES = 4 * T::WORDS * 4;
-  st.c = c; st.num_windows = nw; st.entries = entries; st.total_buckets = nbuckets;
+  st.c = c; st.num_windows = nwd; st.entries = entries; st.total_buckets = nbuckets;
 
   // level-0 slice length: about twice the mean run length (entries per bucket) so that few slices sit entirely inside
   // one run, but never so long that the grid cannot fill the machine
   int KACC = 32;
   {
-    double mean_run = (double)n / (double)B;
+    double mean_run = (double)entries / (double)nbuckets;
     while (KACC < 256 && KACC < 2.0 * mean_run && entries / (size_t)(2 * KACC) >= (size_t)4 * 148 * 256) KACC *= 2;
     if (E.tuning.slice_len > 0) KACC = E.tuning.slice_len;
   }
@@ -215,9 +235,11 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   {
     dim3 grid((unsigned)((n + 255) / 256)), block(256);
     if (fr_mont)
-      k_digits<typename C::FrParams, true><<<grid, block, 0, s>>>((const uint32_t*)d_scalars, (uint32_t)n, plan, (uint32_t*)E.keys_a.ptr, (uint32_t*)E.vals_a.ptr);
+      k_digits<typename C::FrParams, true><<<grid, block, 0, s>>>((const uint32_t*)d_scalars, (uint32_t)n, plan, (uint32_t*)E.keys_a.ptr, (uint32_t*)E.vals_a.ptr,
+                                                                   table_mode ? 0u : B, no_key, (uint32_t)table_stride);
     else
-      k_digits<typename C::FrParams, false><<<grid, block, 0, s>>>((const uint32_t*)d_scalars, (uint32_t)n, plan, (uint32_t*)E.keys_a.ptr, (uint32_t*)E.vals_a.ptr);
+      k_digits<typename C::FrParams, false><<<grid, block, 0, s>>>((const uint32_t*)d_scalars, (uint32_t)n, plan, (uint32_t*)E.keys_a.ptr, (uint32_t*)E.vals_a.ptr,
+                                                                    table_mode ? 0u : B, no_key, (uint32_t)table_stride);
     launches++;
   }
   if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[1], s));
@@ -255,7 +277,7 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   std::vector<size_t> off0(G + 1, 0), off1(G + 1, 0);
   for (int g = 0; g < G; g++) {
     int w0 = g * Wg, w1 = (w0 + Wg < nw) ? w0 + Wg : nw;
-    size_t max_slices = ((size_t)(w1 - w0) * n + KACC - 1) / KACC;
+    size_t max_slices = ((size_t)(w1 - w0) * (table_mode ? entries : n) + KACC - 1) / KACC;
     off0[g + 1] = off0[g] + max_slices;
     off1[g + 1] = off1[g] + (max_slices + KFIX - 1) / KFIX;
   }
@@ -431,12 +453,12 @@ void msm_host(void* r_out, const void* coefs, const void* points, size_t len, bo
 // device-pointer entry (inputs already resident in HBM; used by bench.py `value` and by the cached-bases API)
 template <class C>
 void msm_dev_ptrs(void* r_out, const void* d_coefs, const void* d_points, size_t len, bool fr_mont, int kind, int force_c,
-                  int win_begin, int win_end) {
+                  int win_begin, int win_end, size_t table_stride) {
   Engine& E = engine();
   std::lock_guard<std::mutex> lock(E.mu);
   E.init();
   using HP = host::HXyzz<typename C::H>;
-  HP r = msm_device<C>(E, d_coefs, d_points, len, fr_mont, force_c, win_begin, win_end);
+  HP r = msm_device<C>(E, d_coefs, d_points, len, fr_mont, force_c, win_begin, win_end, nullptr, table_stride);
   write_result<C>(r_out, r, kind);
 }
 

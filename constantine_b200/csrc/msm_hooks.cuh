@@ -143,16 +143,71 @@ int run_scalar_mul_u64(const void* base_aff, const void* k, size_t count, void* 
   return 0;
 }
 
+// table[w][i] = 2^(c*w) * P_i in affine form, w = 0..W-1 (one thread per point; one Fermat inversion per entry -- a
+// one-time cost when bases are cached: ~0.3 s for 2^20 BLS12-381 G1 points).
+template <class T>
+__global__ void __launch_bounds__(128) k_precompute_table(const uint32_t* __restrict__ points, size_t n, int c, int W, uint32_t* table) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Aff<T> P = load_affine<T>(points, (uint32_t)i);
+  const size_t row = n * (size_t)(2 * T::WORDS);
+  {
+    uint32_t* dst = table + i * (2 * T::WORDS);
+    store_words(dst, P.x);
+    store_words(dst + T::WORDS, P.y);
+  }
+  Xyzz<T> q = Xyzz<T>::from_affine(P);
+#pragma unroll 1
+  for (int w = 1; w < W; w++) {
+#pragma unroll 1
+    for (int k = 0; k < c; k++) xyzz_dbl_ni(q);
+    Aff<T> o;
+    if (q.is_inf()) { o.x = T::zero(); o.y = T::zero(); }
+    else {
+      T d; mul_ni(d, q.zz, q.zzz);
+      T di = d.inv();
+      T izz, izzz;
+      mul_ni(izz, di, q.zzz);
+      mul_ni(izzz, di, q.zz);
+      mul_ni(o.x, q.x, izz);
+      mul_ni(o.y, q.y, izzz);
+      // continue from the normalised point: keeps the coordinates small-depth and ZZ = ZZZ = 1
+      q.x = o.x; q.y = o.y; q.zz = T::one(); q.zzz = T::one();
+    }
+    uint32_t* dst = table + (size_t)w * row + i * (2 * T::WORDS);
+    store_words(dst, o.x);
+    store_words(dst + T::WORDS, o.y);
+  }
+}
+
+template <class C>
+void* run_precompute_table(const void* d_points, size_t n, int c, int* W_out) {
+  using T = typename C::T;
+  Engine& E = engine();
+  std::lock_guard<std::mutex> lock(E.mu);
+  E.init();
+  const int W = C::SCALAR_BITS / c + 1;
+  void* table = nullptr;
+  B200_CUDA_CHECK(cudaMalloc(&table, (size_t)W * n * 2 * C::COORD_BYTES + 16));
+  k_precompute_table<T><<<(unsigned)((n + 127) / 128), 128, 0, E.stream>>>((const uint32_t*)d_points, n, c, W, (uint32_t*)table);
+  B200_CUDA_CHECK(cudaGetLastError());
+  B200_CUDA_CHECK(cudaStreamSynchronize(E.stream));
+  *W_out = W;
+  return table;
+}
+
 // explicit instantiation of everything the C ABI needs for one curve (one translation unit per curve)
 #define B200_INSTANTIATE_CURVE(DESC)                                                                              \
   template void msm_host<DESC>(void*, const void*, const void*, size_t, bool, int);                               \
-  template void msm_dev_ptrs<DESC>(void*, const void*, const void*, size_t, bool, int, int, int, int);            \
+  template void msm_dev_ptrs<DESC>(void*, const void*, const void*, size_t, bool, int, int, int, int, size_t);    \
+  template void* run_precompute_table<DESC>(const void*, size_t, int, int*);                                      \
   template int run_test_ec_op<DESC>(int, void*, const void*, const void*, size_t);                                \
   template int run_sum_partials<DESC>(int, void*, const void*, size_t);                                           \
   template int run_scalar_mul_u64<DESC>(const void*, const void*, size_t, void*);
 #define B200_DECLARE_CURVE(DESC)                                                                                  \
   extern template void msm_host<DESC>(void*, const void*, const void*, size_t, bool, int);                        \
-  extern template void msm_dev_ptrs<DESC>(void*, const void*, const void*, size_t, bool, int, int, int, int);     \
+  extern template void msm_dev_ptrs<DESC>(void*, const void*, const void*, size_t, bool, int, int, int, int, size_t); \
+  extern template void* run_precompute_table<DESC>(const void*, size_t, int, int*);                               \
   extern template int run_test_ec_op<DESC>(int, void*, const void*, const void*, size_t);                         \
   extern template int run_sum_partials<DESC>(int, void*, const void*, size_t);                                    \
   extern template int run_scalar_mul_u64<DESC>(const void*, const void*, size_t, void*);

@@ -69,9 +69,13 @@ __device__ __forceinline__ void window_digit(const uint32_t* k, const DigitPlan&
 
 // One thread per scalar. FR_MONT: scalars arrive as Fr Montgomery residues and are first converted to canonical
 // integers by one Montgomery reduction (multiplication by the integer 1), like the reference's fromField pass.
+// key = w_local * key_stride + bucket  (key_stride = B normally; 0 when all windows share one bucket set because the
+// points come from a table of precomputed window multiples), val = (w_local * val_stride + i) | sign << 31
+// (val_stride = 0 normally: every window references point i; = table row length in table mode).
 template <class FrParams, bool FR_MONT>
 __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ scalars, uint32_t n, DigitPlan plan,
-                                                uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                uint32_t key_stride, uint32_t no_key, uint32_t val_stride) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t k[8];
@@ -83,13 +87,13 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
     uint32_t one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
     fe_mul<FrParams>(k, k, one);
   }
-  const int nw = plan.win_end - plan.win_begin;
   for (int w = plan.win_begin; w < plan.win_end; w++) {
     uint32_t val, neg;
     window_digit(k, plan, w, val, neg);
-    size_t slot = (size_t)(w - plan.win_begin) * n + i;
-    keys[slot] = val ? (uint32_t)(w - plan.win_begin) * plan.buckets_per_window + (val - 1u) : (uint32_t)nw * plan.buckets_per_window;
-    vals[slot] = i | (neg << 31);
+    const uint32_t wl = (uint32_t)(w - plan.win_begin);
+    size_t slot = (size_t)wl * n + i;
+    keys[slot] = val ? wl * key_stride + (val - 1u) : no_key;
+    vals[slot] = (wl * val_stride + i) | (neg << 31);
   }
 }
 

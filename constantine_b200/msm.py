@@ -122,6 +122,13 @@ class CachedBases:
         self.n = length if length is not None else len(memoryview(points).cast("B")) // self.curve.aff_bytes
         self._h = _lib.load().ctt_b200_bases_upload(self.curve.curve_id, _buf(points), self.n)
 
+    def precompute(self, c: int = 0) -> int:
+        """One-time table of window multiples 2^(c w) P_i (ctt_b200_bases_precompute); returns the window size used."""
+        rc = _lib.load().ctt_b200_bases_precompute(self._h, c)
+        if rc < 0:
+            raise ValueError("ctt_b200_bases_precompute failed")
+        return rc
+
     def msm(self, coefs, length=None, out=OUT_JAC, coef_kind="big") -> bytes:
         n = length if length is not None else len(memoryview(coefs).cast("B")) // 32
         r = ctypes.create_string_buffer(self.curve.jac_bytes)

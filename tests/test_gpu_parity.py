@@ -260,3 +260,78 @@ def test_adversarial_distribution_large(M, lib, tp):
         scal = np.frombuffer(s.to_bytes(32, "little") * n, dtype=np.uint8).reshape(n, 32)
         want = pyref.ec_mul_fast((s * ksum) % cv.fr.modulus, cv.gen, cv)
         assert pyref.jac_bytes_to_affine(M.multi_scalar_mul_vartime_parallel(tp, cv, scal, pts, n), cv) == want
+
+
+def test_concurrent_callers_are_serialised(M, oracle_lib):
+    """The reference allows nested / concurrent MSM calls (SURVEY.md 8b "Threading"); the engine serialises them with a
+    mutex. Four Python threads hammer the C symbol with different inputs; every result must match its own oracle value."""
+    import threading
+    cv = CURVES["bn254_snarks_g1"]
+    _, pool = point_pool(cv)
+    jobs = []
+    for seed in range(4):
+        r = random.Random(seed)
+        n = 500 + 137 * seed
+        pts = [pool[r.randrange(len(pool))] for _ in range(n)]
+        ks = [r.getrandbits(254) for _ in range(n)]
+        cb, pb = pack(cv, ks, pts)
+        jobs.append((cb, pb, n, pyref.jac_bytes_to_affine(oracle_lib.msm(cv, cb, pb, n), cv)))
+    errors = []
+
+    def worker(job):
+        cb, pb, n, want = job
+        tp = M.Threadpool.new(1)
+        for _ in range(5):
+            got = pyref.jac_bytes_to_affine(M.multi_scalar_mul_vartime_parallel(tp, cv, cb, pb, n), cv)
+            if got != want:
+                errors.append(n)
+        tp.shutdown()
+
+    threads = [threading.Thread(target=worker, args=(j,)) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors
+
+
+def test_closed_form_2_22(M, lib, tp):
+    """N = 2^22 (the largest BASELINE size), Pallas through the fr_coefs entry (config 4's symbol)."""
+    cv = CURVES["pallas_ec"]
+    n = 1 << 22
+    rng = np.random.default_rng(22)
+    k = rng.integers(1, 2**63, size=n, dtype=np.uint64)
+    pts = _gen_points(lib, cv, k)
+    r = cv.fr.modulus
+    s_lo = rng.integers(0, 2**63, size=n, dtype=np.uint64)
+    # scalars s_i = s_lo_i * 2^190 + 1 (mod r), passed as Fr Montgomery residues
+    s_int = [((int(a) << 190) + 1) % r for a in s_lo]
+    scal = np.frombuffer(b"".join(((s * cv.fr.R) % r).to_bytes(32, "little") for s in s_int), dtype=np.uint8).reshape(n, 32)
+    total = sum(a * int(b) for a, b in zip(s_int, k)) % r
+    want = pyref.ec_mul_fast(total, cv.gen, cv)
+    got = M.multi_scalar_mul_vartime_parallel(tp, cv, scal, pts, n, out="prj", coef_kind="fr")
+    assert pyref.prj_bytes_to_affine(got, cv) == want
+
+
+def test_cached_bases_with_precomputed_table(M, oracle_lib, rng):
+    """ctt_b200_bases_precompute: window multiples 2^(c w) P_i cached on the device, all windows share one bucket set.
+    Same results as the plain path for every prefix length, both scalar encodings, several window sizes."""
+    for curve, n in (("bls12_381_g1", 3000), ("bn254_snarks_g1", 4097), ("bls12_381_g2", 600)):
+        cv = CURVES[curve]
+        _, pool = point_pool(cv)
+        pts = [pool[rng.randrange(len(pool))] for _ in range(n)]
+        pts[7] = None
+        _, pb = pack(cv, [], pts)
+        bases = M.CachedBases(cv, pb, n)
+        for c in (0, 8, 13):
+            used = bases.precompute(c)
+            assert 2 <= used <= 20
+            for m in (n, n // 2, 1):
+                ks = [rng.getrandbits(cv.scalar_bits) for _ in range(m)]
+                cb, _ = pack(cv, ks, [])
+                want = pyref.jac_bytes_to_affine(oracle_lib.msm(cv, cb, pb[:m * cv.aff_bytes], m), cv)
+                assert pyref.jac_bytes_to_affine(bases.msm(cb, m), cv) == want, (curve, c, m)
+                cbm, _ = pack(cv, [k % cv.fr.modulus for k in ks], [], fr_mont=True)
+                got = pyref.prj_bytes_to_affine(bases.msm(cbm, m, out=M.OUT_PRJ, coef_kind="fr"), cv)
+                assert got == want, (curve, c, m, "fr")
+        bases.free()
