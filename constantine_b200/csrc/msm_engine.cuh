@@ -91,7 +91,8 @@ inline int choose_window_table(size_t n, int bits) {
   int best_c = 2;
   for (int c = 2; c <= 20; c++) {
     int W = bits / c + 1;
-    double cost = (double)W * (double)n * 10.0 + (double)(1u << (c - 1)) * 80.0;
+    // one bucket set only: its reduction is latency-bound (~1 ms at 2^17 buckets), hence the heavier bucket weight
+    double cost = (double)W * (double)n * 10.0 + (double)(1u << (c - 1)) * 400.0;
     if ((double)W * (double)n >= 2147483648.0) continue;
     if (cost < best) { best = cost; best_c = c; }
   }
