@@ -224,6 +224,7 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   {
     double mean_run = (double)entries / (double)nbuckets;
     while (KACC < 256 && KACC < 2.0 * mean_run && entries / (size_t)(2 * KACC) >= (size_t)4 * 148 * 256) KACC *= 2;
+    if (entries / 32 < (size_t)2 * 148 * 256) KACC = 16;   // fewer than two waves of slices: halve them so the SMs fill evenly
     if (E.tuning.slice_len > 0) KACC = E.tuning.slice_len;
   }
   cudaStream_t s = E.compute();

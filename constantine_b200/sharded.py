@@ -29,16 +29,37 @@ def window_range(num_windows: int, world: int, rank: int) -> Tuple[int, int]:
     return balanced_chunk(num_windows, world, rank)
 
 
+_xchg_cache = {}
+
+
 def _all_gather_bytes(payload: bytes, group=None, device=None) -> list:
+    """all_gather of one small fixed-size byte string per rank. Buffers (pinned host staging + device tensors for NCCL)
+    are created once per (size, device) and reused: the exchange is latency-bound, allocations would dominate it."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    t = torch.frombuffer(bytearray(payload), dtype=torch.uint8)
-    if device is not None:
-        t = t.to(device)
-    outs = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(outs, t, group=group)
-    return [bytes(o.cpu().numpy().tobytes()) for o in outs]
+    n = len(payload)
+    key = (n, str(device), world, id(group))
+    buf = _xchg_cache.get(key)
+    if buf is None:
+        if device is None:
+            buf = (torch.empty(n, dtype=torch.uint8), torch.empty(world * n, dtype=torch.uint8), None, None)
+        else:
+            buf = (torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(world * n, dtype=torch.uint8).pin_memory(),
+                   torch.empty(n, dtype=torch.uint8, device=device), torch.empty(world * n, dtype=torch.uint8, device=device))
+        _xchg_cache[key] = buf
+    h_in, h_out, d_in, d_out = buf
+    h_in.numpy()[:] = memoryview(payload)
+    if device is None:
+        dist.all_gather_into_tensor(h_out, h_in, group=group) if hasattr(dist, "all_gather_into_tensor") and dist.get_backend(group) != "gloo" \
+            else dist.all_gather(list(h_out.view(world, n).unbind(0)), h_in, group=group)
+    else:
+        d_in.copy_(h_in, non_blocking=True)
+        dist.all_gather_into_tensor(d_out, d_in, group=group)
+        h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+    raw = h_out.numpy().tobytes()
+    return [raw[i * n:(i + 1) * n] for i in range(world)]
 
 
 def combine_partials(curve, partials: list, out=_msm.OUT_JAC) -> bytes:
