@@ -32,9 +32,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-CURVE = "bls12_381_g1"
+CURVE = "bls12_381_g1"                   # default workload; --curve selects another BASELINE config (same harness)
 INT_MACS_PER_POINT_ADD = 3300            # 11 field mults x (2*12^2 + 12) MACs, BLS12-381 G1
 ALGO_BYTES_PER_TERM = 128                # 32 B scalar + 96 B affine point
+# SURVEY.md 8d per-unit figures for the other groups: (int-MACs per point-add, algorithmic bytes per term)
+UNIT_FIGURES = {"bls12_381_g1": (3300, 128), "bn254_snarks_g1": (1496, 96), "pallas_ec": (1496, 96), "vesta_ec": (1496, 96),
+                "bls12_381_g2": (9000, 224), "bn254_snarks_g2": (4080, 160)}
 # Measured on this pool's B200 (tools/ubench.cu, profiles/ubench_r1.jsonl): the integer multiplier issues 63.4 IMAD /clk/SM,
 # i.e. one 32-bit result half per lane per pass; a full 32x32->64 multiply-accumulate (IMAD.WIDE.U32 with 64-bit addend
 # or carry, what mad.lo.cc/madc.hi.cc pairs compile to) takes two passes: measured 31.65 MAC/clk/SM
@@ -99,7 +102,7 @@ def make_inputs(n, seed):
     cv = CURVES[CURVE]
     rng = np.random.default_rng(seed)
     scal = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
-    scal[:, 31] &= 0x7F
+    scal[:, 31] &= (1 << (cv.scalar_bits - 248)) - 1
     k = rng.integers(1, 2**63, size=n, dtype=np.uint64)
     gen = np.frombuffer(_gen_bytes(cv), dtype=np.uint8).copy()
     pts = np.empty((n, cv.aff_bytes), dtype=np.uint8)
@@ -222,7 +225,11 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--logn", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--curve", default="bls12_381_g1", help="bls12_381_g1 (default, BASELINE metric) | pallas_ec | bls12_381_g2 | ...")
     args = ap.parse_args()
+    global CURVE, INT_MACS_PER_POINT_ADD, ALGO_BYTES_PER_TERM
+    CURVE = args.curve
+    INT_MACS_PER_POINT_ADD, ALGO_BYTES_PER_TERM = UNIT_FIGURES[CURVE]
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
@@ -236,6 +243,11 @@ def main():
 
     rank, world, local = dist_env()
     cv = CURVES[CURVE]
+    # NCCL prints its version banner on stdout at the first collective: keep stdout clean for the ONE JSON line by
+    # pointing fd 1 at stderr until the result is printed
+    sys.stdout.flush()
+    saved_stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -269,7 +281,8 @@ def main():
         part = M.msm_device_ptrs(cv, d_scal.data_ptr(), d_pts.data_ptr(), n, out=M.OUT_XYZZ, force_c=c_plan, win_begin=wb, win_end=we)
         return sharded.msm_point_sharded(cv, part, device=dev)
 
-    named = _lib.named_msm("ctt_bls12_381_g1_jac_multi_scalar_mul_big_coefs_vartime_parallel")
+    symbol = f"ctt_{cv.cprefix}_jac_multi_scalar_mul_big_coefs_vartime_parallel"
+    named = _lib.named_msm(symbol)
     named_xyzz = lib.ctt_b200_msm_host
     tp = M.Threadpool.new(1)
     r_buf = ctypes.create_string_buffer(4 * cv.coord_bytes)
@@ -350,12 +363,13 @@ def main():
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     algo_bytes = n * ALGO_BYTES_PER_TERM
     hbm_achieved = algo_bytes / (ms_res * 1e-3) / 1e9
-    padds = algorithmic_point_adds(n, st["c"])
+    padds = algorithmic_point_adds(n, st["c"], cv.scalar_bits)
     line = {
-        "metric": "bls12_381_g1_msm_throughput", "value": 1e3 / ms_res, "unit": "MSM/s", "n_gpus": world, "steps": args.steps,
+        "metric": f"{CURVE}_msm_throughput", "value": 1e3 / ms_res, "unit": "MSM/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": f"BLS12-381 G1 MSM N=2^{args.logn} (BASELINE configs[2]), uniform 255-bit scalars, subgroup points",
+        "config": {"workload": (f"BLS12-381 G1 MSM N=2^{args.logn} (BASELINE configs[2]), uniform 255-bit scalars, subgroup points"
+                                if CURVE == "bls12_381_g1" else f"{CURVE} MSM N=2^{args.logn}, uniform {cv.scalar_bits}-bit scalars, subgroup points"),
                    "parallelism": "1 GPU" if world == 1 else (f"resident leg: inputs replicated, {W_plan} windows sharded over {world} GPUs; "
                                                                   f"e2e leg: points sharded over {world} GPUs; both + all_gather of partial points"),
                    "window_c": st["c"], "windows": st["num_windows"],
@@ -364,7 +378,7 @@ def main():
         "wall_ms_per_step": wall_res,
         "e2e": {"value": 1e3 / ms_e2e, "unit": "MSM/s", "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e,
                 "h2d_bytes_per_step": int(n_loc * ALGO_BYTES_PER_TERM), "d2h_bytes_per_step": int(st["num_windows"] * 4 * cv.coord_bytes),
-                "api": "ctt_bls12_381_g1_jac_multi_scalar_mul_big_coefs_vartime_parallel (pinned host buffers)"},
+                "api": symbol + " (pinned host buffers)"},
         "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
         "phases_ms_serial_launch_order": {k: round(sum(s[k] for s in serial_stats) / len(serial_stats), 4) for k in
                                           ("ms_digits", "ms_sort", "ms_accumulate", "ms_fixup", "ms_reduce", "ms_d2h_tail", "ms_total")},
@@ -372,7 +386,7 @@ def main():
         "roofline": {"bound": "int32-mad (neither hbm nor tensor: see roofline_hbm)", "kernel": "k_accumulate",
                      "achieved": achieved / 1e12, "peak": INT_MAC_PEAK_PER_S / 1e12, "unit": "TMAC/s (32x32->64)",
                      "frac": achieved / INT_MAC_PEAK_PER_S,
-                     "traffic": (NCU_TRAFFIC_BYTES_N20 if (world == 1 and args.logn == 20 and st["c"] == 16) else None),
+                     "traffic": (NCU_TRAFFIC_BYTES_N20 if (world == 1 and args.logn == 20 and st["c"] == 16 and CURVE == "bls12_381_g1") else None),
                      "traffic_note": "DRAM bytes of one k_accumulate launch from profiles/ncu_k_accumulate_r1.txt; algorithmic gather = entries x 96 B = 1.61e9 B",
                      "fmaheavy_pipe_busy_ncu": 0.82,
                      "peak_source": "measured 32x32->64 MAC rate (IMAD.WIDE.U32.X chains, 31.65/clk/SM x 148 SM x 1.965 GHz), tools/ubench.cu -> profiles/ubench_r1.jsonl",
@@ -381,9 +395,12 @@ def main():
                          "traffic": None, "peak_source": hbm_src, "algorithmic_bytes": algo_bytes},
         "clocks": clocks, "paths_agree": bool(same),
     }
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and CURVE == "bls12_381_g1":
         line["cpu_baseline"] = {k: v for k, v in time_oracle(n).items() if k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout_fd, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

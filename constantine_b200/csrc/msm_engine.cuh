@@ -292,8 +292,10 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   uint32_t L = (uint32_t)E.tuning.reduce_chunk;
   if (L < 1) L = 1;
   uint32_t chunks = (B + L - 1) / L;
-  // small bucket counts: keep at least ~2 warps per SM worth of chunk threads
-  while (L > 1 && (size_t)chunks * nw < (size_t)E.sm_count * 64 && chunks < B) { L = (L + 1) / 2; chunks = (B + L - 1) / L; }
+  // small bucket counts: the phase is a chain of dependent point operations, so trade chunk length for more threads
+  // (x4 for Fp2 coordinates, whose point operations are ~4x slower)
+  const size_t want_threads = (size_t)E.sm_count * 64 * (T::WORDS > 12 ? 4 : 1);
+  while (L > 1 && (size_t)chunks * nw < want_threads && chunks < B) { L = (L + 1) / 2; chunks = (B + L - 1) / L; }
   int nbits = 0;
   while (nbits < 32 && ((uint64_t)(chunks - 1) * L >> nbits) != 0) nbits++;
   E.red_a.ensure((size_t)chunks * nw * XYZZ_BYTES);
