@@ -14,7 +14,7 @@
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use this library.
  *
- * Build: see oracle/Makefile  (gcc -O3 -march=native -shared -fPIC -pthread).
+ * Build: see oracle/Makefile  (gcc -O3 -march=x86-64-v3 -shared -fPIC -pthread).
  */
 #include <stdint.h>
 #include <stdlib.h>
