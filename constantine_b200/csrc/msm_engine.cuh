@@ -293,8 +293,8 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   if (L < 1) L = 1;
   uint32_t chunks = (B + L - 1) / L;
   // small bucket counts: the phase is a chain of dependent point operations, so trade chunk length for more threads
-  // (x4 for Fp2 coordinates, whose point operations are ~4x slower)
-  const size_t want_threads = (size_t)E.sm_count * 64 * (T::WORDS > 12 ? 4 : 1);
+  // (a larger target for Fp2 was measured slower: the offset multiplication per chunk dominates then)
+  const size_t want_threads = (size_t)E.sm_count * 64;
   while (L > 1 && (size_t)chunks * nw < want_threads && chunks < B) { L = (L + 1) / 2; chunks = (B + L - 1) / L; }
   int nbits = 0;
   while (nbits < 32 && ((uint64_t)(chunks - 1) * L >> nbits) != 0) nbits++;
