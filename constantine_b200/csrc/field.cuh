@@ -194,6 +194,69 @@ B200_DEV void fe_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   for (int k = 0; k < N; k++) r[k] = t[k];
 }
 
+// Same multiplication with the outer loop kept ROLLED (two CIOS steps per iteration, the multiplier limbs rotated through
+// registers so every index stays static): one third of the code of the fully unrolled form. Experiment for the
+// instruction-fetch stalls ncu shows in k_accumulate (profiles/ncu_k_accumulate_r1.txt); selected with -DB200_ROLLED_MUL.
+template <class F>
+B200_DEV void fe_mul_rolled(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  constexpr int N = F::N;
+  static_assert(N % 2 == 0 && N >= 4, "even limb count");
+  uint32_t A[N], B[N];
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+    A[j] = p_mul_lo(a[j], b[0]);
+    A[j + 1] = p_mul_hi(a[j], b[0]);
+    B[j] = p_mul_lo(a[j + 1], b[0]);
+    B[j + 1] = p_mul_hi(a[j + 1], b[0]);
+  }
+  mont_round<F>(A, B);
+  uint32_t bb[N];  // bb[0], bb[1] are the next two multiplier limbs
+#pragma unroll
+  for (int j = 0; j < N - 1; j++) bb[j] = b[j + 1];
+  bb[N - 1] = 0;
+#pragma unroll 1
+  for (int it = 0; it < (N - 2) / 2; it++) {
+    mont_step<F>(B, A, a, bb[0]);   // odd step
+    mont_step<F>(A, B, a, bb[1]);   // even step
+#pragma unroll
+    for (int j = 0; j < N - 2; j++) bb[j] = bb[j + 2];
+  }
+  mont_step<F>(B, A, a, bb[0]);     // last (odd) step, i = N-1
+  uint32_t t[N];
+  t[0] = p_add_cc(A[0], B[1]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) t[k] = p_addc_cc(A[k], B[k + 1]);
+  t[N - 1] = p_addc(A[N - 1], 0);
+  final_sub<F>(t);
+#pragma unroll
+  for (int k = 0; k < N; k++) r[k] = t[k];
+}
+
+// Fully uniform rolled form: N/2 iterations of [even step, odd step] starting from zero rows (the first step then
+// computes 0 + a*b[0] at the price of a few additions with zero); smallest code.
+template <class F>
+B200_DEV void fe_mul_rolled2(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  constexpr int N = F::N;
+  uint32_t A[N], B[N], bb[N];
+#pragma unroll
+  for (int j = 0; j < N; j++) { A[j] = 0; B[j] = 0; bb[j] = b[j]; }
+#pragma unroll 1
+  for (int it = 0; it < N / 2; it++) {
+    mont_step<F>(A, B, a, bb[0]);   // even step (i = 2 it)
+    mont_step<F>(B, A, a, bb[1]);   // odd step  (i = 2 it + 1)
+#pragma unroll
+    for (int j = 0; j < N - 2; j++) bb[j] = bb[j + 2];
+  }
+  uint32_t t[N];
+  t[0] = p_add_cc(A[0], B[1]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) t[k] = p_addc_cc(A[k], B[k + 1]);
+  t[N - 1] = p_addc(A[N - 1], 0);
+  final_sub<F>(t);
+#pragma unroll
+  for (int k = 0; k < N; k++) r[k] = t[k];
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Value types with a common interface (zero/one/is_zero/==, +, -, *, sqr, neg, dbl) so that the
 // elliptic-curve code is written once for G1 (Fp) and G2 (Fp2).
@@ -231,8 +294,21 @@ struct Fp {
   }
   B200_DEV Fp operator+(const Fp& b) const { Fp r; fe_add<F>(r.l, l, b.l); return r; }
   B200_DEV Fp operator-(const Fp& b) const { Fp r; fe_sub<F>(r.l, l, b.l); return r; }
-  B200_DEV Fp operator*(const Fp& b) const { Fp r; fe_mul<F>(r.l, l, b.l); return r; }
-  B200_DEV Fp sqr() const { Fp r; fe_mul<F>(r.l, l, l); return r; }
+  // 12-limb fields use a rolled outer loop (one third of the code): the fully unrolled 381-bit multiplier makes the
+  // mixed-add body overflow the instruction caches (measured: +9.6 % mixed adds/s rolled, -5 % on a bare multiply chain;
+  // 8-limb fields are faster unrolled). B200_MUL_VARIANT forces 0 = unrolled, 1 = rolled, 2 = uniform rolled.
+#ifndef B200_MUL_VARIANT
+#define B200_MUL_VARIANT (-1)
+#endif
+  B200_DEV Fp operator*(const Fp& b) const {
+    Fp r;
+    constexpr int V = (B200_MUL_VARIANT >= 0) ? B200_MUL_VARIANT : (N >= 12 ? 1 : 0);
+    if constexpr (V == 2) fe_mul_rolled2<F>(r.l, l, b.l);
+    else if constexpr (V == 1) fe_mul_rolled<F>(r.l, l, b.l);
+    else fe_mul<F>(r.l, l, b.l);
+    return r;
+  }
+  B200_DEV Fp sqr() const { return (*this) * (*this); }
   B200_DEV Fp neg() const { Fp r; fe_neg<F>(r.l, l); return r; }
   B200_DEV Fp dbl() const { Fp r; fe_add<F>(r.l, l, l); return r; }
   // this = cond ? -this : this
