@@ -150,8 +150,8 @@ B200_DEV void xyzz_madd(Xyzz<T>& acc, const Aff<T>& q) {
     acc.x = q.x; acc.y = q.y; acc.zz = T::one(); acc.zzz = T::one();
     return;
   }
-  T U2 = q.x * acc.zz;
-  T S2 = q.y * acc.zzz;
+  T U2 = q.x.mul_u(acc.zz);
+  T S2 = q.y.mul_u(acc.zzz);
   T P = U2 - acc.x;
   T R = S2 - acc.y;
   if (P.is_zero()) {
@@ -162,15 +162,15 @@ B200_DEV void xyzz_madd(Xyzz<T>& acc, const Aff<T>& q) {
     else acc = Xyzz<T>::inf();
     return;
   }
-  T PP = P.sqr();
-  T PPP = P * PP;
-  T Q = acc.x * PP;
-  T X3 = R.sqr() - PPP - Q.dbl();
-  T Y3 = R * (Q - X3) - acc.y * PPP;
+  T PP = P.sqr_u();
+  T PPP = P.mul_u(PP);
+  T Q = acc.x.mul_u(PP);
+  T X3 = R.sqr_u() - PPP - Q.dbl();
+  T Y3 = R.mul_u(Q - X3) - acc.y.mul_u(PPP);
   acc.x = X3;
   acc.y = Y3;
-  acc.zz = acc.zz * PP;
-  acc.zzz = acc.zzz * PPP;
+  acc.zz = acc.zz.mul_u(PP);
+  acc.zzz = acc.zzz.mul_u(PPP);
 }
 
 // acc += q  (both XYZZ): add-2008-s, 12M + 2S on the generic path.
