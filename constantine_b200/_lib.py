@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libctt_b200_msm.so")
+LIB_PATH = os.environ.get("CTT_B200_LIB", os.path.join(_HERE, "lib", "libctt_b200_msm.so"))   # override: experiments with variant builds
 _lib = None
 
 

@@ -150,6 +150,10 @@ B200_DEV void xyzz_madd(Xyzz<T>& acc, const Aff<T>& q) {
     acc.x = q.x; acc.y = q.y; acc.zz = T::one(); acc.zzz = T::one();
     return;
   }
+#ifdef B200_MADD_ROLLED
+#define mul_u operator*
+#define sqr_u sqr
+#endif
   T U2 = q.x.mul_u(acc.zz);
   T S2 = q.y.mul_u(acc.zzz);
   T P = U2 - acc.x;
@@ -171,6 +175,10 @@ B200_DEV void xyzz_madd(Xyzz<T>& acc, const Aff<T>& q) {
   acc.y = Y3;
   acc.zz = acc.zz.mul_u(PP);
   acc.zzz = acc.zzz.mul_u(PPP);
+#ifdef B200_MADD_ROLLED
+#undef mul_u
+#undef sqr_u
+#endif
 }
 
 // acc += q  (both XYZZ): add-2008-s, 12M + 2S on the generic path.
