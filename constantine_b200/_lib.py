@@ -65,6 +65,10 @@ def load():
     if hasattr(lib, "ctt_b200_scalar_mul_u64"):
         lib.ctt_b200_scalar_mul_u64.argtypes = [ci, vp, vp, sz, vp]
         lib.ctt_b200_scalar_mul_u64.restype = ci
+    for nm in ("ctt_eth_evm_bls12381_g1msm", "ctt_eth_evm_bls12381_g2msm"):
+        fn = getattr(lib, nm)
+        fn.argtypes = [vp, sz, vp, sz]
+        fn.restype = ctypes.c_ubyte
     lib.ctt_threadpool_new.argtypes = [ci]
     lib.ctt_threadpool_new.restype = vp
     lib.ctt_threadpool_shutdown.argtypes = [vp]

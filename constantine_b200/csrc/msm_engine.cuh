@@ -309,7 +309,7 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
     const size_t max_slices = off0[g + 1] - off0[g];
     // 3. accumulate (main stream)
     {
-      dim3 block(128), grid((unsigned)((max_slices + 127) / 128));
+      dim3 block(B200_ACC_THREADS), grid((unsigned)((max_slices + B200_ACC_THREADS - 1) / B200_ACC_THREADS));
       k_accumulate<T><<<grid, block, 0, s>>>(keys, vals, (const unsigned long long*)E.bounds.ptr, w0, w1, no_key, (const uint32_t*)d_points,
                                              (uint32_t*)E.buckets.ptr, (uint32_t*)E.part_pts[0].ptr + off0[g] * XW,
                                              (uint32_t*)E.part_keys[0].ptr + off0[g], max_slices, KACC);

@@ -110,15 +110,18 @@ constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 #ifndef B200_ACC_MIN_BLOCKS
 #define B200_ACC_MIN_BLOCKS 2
 #endif
+#ifndef B200_ACC_THREADS
+#define B200_ACC_THREADS 128
+#endif
 template <class T>
-__global__ void __launch_bounds__(128, (T::WORDS <= 12) ? B200_ACC_MIN_BLOCKS : 1)
+__global__ void __launch_bounds__(B200_ACC_THREADS, (T::WORDS <= 12) ? B200_ACC_MIN_BLOCKS : 1)
 k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const unsigned long long* __restrict__ bounds,
              int w0, int w1, uint32_t no_key, const uint32_t* __restrict__ points, uint32_t* buckets, uint32_t* part_pts,
              uint32_t* part_keys, size_t max_slices, int K) {
   // entries of windows [w0, w1) occupy sorted positions [begin, total); slices are counted from `begin`
   const size_t begin = (size_t)bounds[w0], total = (size_t)bounds[w1];
   const size_t num_slices = (total - begin + (size_t)K - 1) / (size_t)K;
-  __shared__ uint32_t head_smem[128 * 4 * T::WORDS];
+  __shared__ uint32_t head_smem[B200_ACC_THREADS * 4 * T::WORDS];
   const unsigned lane = threadIdx.x & 31u;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = t < num_slices;

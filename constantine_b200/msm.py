@@ -141,3 +141,22 @@ class CachedBases:
         if self._h:
             _lib.load().ctt_b200_bases_free(self._h)
             self._h = None
+
+
+EVM_STATUS = ("cttEVM_Success", "cttEVM_InvalidInputSize", "cttEVM_InvalidOutputSize", "cttEVM_IntLargerThanModulus",
+              "cttEVM_PointNotOnCurve", "cttEVM_PointNotInSubgroup", "cttEVM_VerificationFailure")
+
+
+def eth_evm_bls12381_g1msm(inputs: bytes, out_len: int = 128):
+    """EIP-2537 BLS12_G1MSM through ctt_eth_evm_bls12381_g1msm (reference constantine/ethereum_evm_precompiles.nim:894-975).
+    Returns (status name, output bytes)."""
+    r = ctypes.create_string_buffer(out_len)
+    st = _lib.load().ctt_eth_evm_bls12381_g1msm(r, out_len, bytes(inputs), len(inputs))
+    return EVM_STATUS[st], r.raw
+
+
+def eth_evm_bls12381_g2msm(inputs: bytes, out_len: int = 256):
+    """EIP-2537 BLS12_G2MSM through ctt_eth_evm_bls12381_g2msm (reference constantine/ethereum_evm_precompiles.nim:977-1060)."""
+    r = ctypes.create_string_buffer(out_len)
+    st = _lib.load().ctt_eth_evm_bls12381_g2msm(r, out_len, bytes(inputs), len(inputs))
+    return EVM_STATUS[st], r.raw

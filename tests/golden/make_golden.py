@@ -58,7 +58,8 @@ def eip2537(path, curve):
         assert all(pyref.on_curve(P, curve) for P in pts) and pyref.on_curve(want, curve)
         assert pyref.msm_naive_fast(ks, pts, curve) == want, t["Name"]  # the exact tier agrees with the reference's vector
         cases.append({"name": t["Name"], "curve": curve.name, "source": os.path.relpath(path, "/root/reference"),
-                      "scalars": [hx(k) for k in ks], "points": [enc_point(P) for P in pts], "expected": enc_point(want)})
+                      "scalars": [hx(k) for k in ks], "points": [enc_point(P) for P in pts], "expected": enc_point(want),
+                      "raw_input": t["Input"], "raw_expected": t["Expected"]})
     return cases
 
 
@@ -87,9 +88,15 @@ def sage_file(path, curve):
 
 
 def main():
-    out = {"eip2537": [], "sage_scalar_mul": []}
+    out = {"eip2537": [], "eip2537_fail": [], "sage_scalar_mul": []}
     out["eip2537"] += eip2537(f"{REF}/protocol_ethereum_evm_precompiles/eip-2537/multiexp_G1_bls.json", CURVES["bls12_381_g1"])
     out["eip2537"] += eip2537(f"{REF}/protocol_ethereum_evm_precompiles/eip-2537/multiexp_G2_bls.json", CURVES["bls12_381_g2"])
+    out["eip2537_fail"] = []
+    for g in ("G1", "G2"):
+        path = f"{REF}/protocol_ethereum_evm_precompiles/eip-2537/fail-multiexp_{g}_bls.json"
+        for t in json.load(open(path)):
+            out["eip2537_fail"].append({"name": t["Name"], "group": g, "raw_input": t["Input"], "expected_error": t["ExpectedError"],
+                                        "source": os.path.relpath(path, "/root/reference")})
     files = [("BLS12_381", "G1", "bls12_381_g1", (32, 64, 128, 255)), ("BLS12_381", "G2", "bls12_381_g2", (32, 64, 128, 255)),
              ("BN254_Snarks", "G1", "bn254_snarks_g1", (32, 64, 128, 254)), ("BN254_Snarks", "G2", "bn254_snarks_g2", (32, 64, 128, 254)),
              ("Pallas", "G1", "pallas_ec", (255,)), ("Vesta", "G1", "vesta_ec", (255,))]
