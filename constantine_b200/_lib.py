@@ -52,6 +52,8 @@ def load():
     lib.ctt_b200_last_stats.restype = None
     lib.ctt_b200_set_tuning.argtypes = [ci, ci, ci]
     lib.ctt_b200_set_tuning.restype = None
+    lib.ctt_b200_set_concurrency.argtypes = [ci]
+    lib.ctt_b200_set_concurrency.restype = None
     lib.ctt_b200_set_groups.argtypes = [ci]
     lib.ctt_b200_set_groups.restype = None
     lib.ctt_b200_set_stream.argtypes = [vp]

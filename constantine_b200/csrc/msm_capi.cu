@@ -139,30 +139,26 @@ int ctt_b200_bases_precompute(ctt_b200_bases* bases, int c) {
 int ctt_b200_msm_cached_bases(const ctt_b200_bases* bases, int out_kind, void* r, const void* coefs, size_t len, int fr_mont) {
   const Bases* b = reinterpret_cast<const Bases*>(bases);
   if (!b || len > b->len) return -1;
-  Engine& E = engine();
-  {
-    std::lock_guard<std::mutex> lock(E.mu);
-    E.init();
-    E.d_scalars.ensure(len * 32 + 16);
-    B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, len * 32, cudaMemcpyHostToDevice, E.compute()));
-    B200_CUDA_CHECK(cudaStreamSynchronize(E.compute()));
-  }
-  if (b->d_table) {
-    switch (b->curve_id) {
-#define X(ID, DESC) case ID: msm_dev_ptrs<DESC>(r, E.d_scalars.ptr, b->d_table, len, fr_mont != 0, out_kind, b->table_c, 0, -1, b->len); return 0;
-      B200_FOR_EACH_CURVE(X)
+  const void* pts = b->d_table ? b->d_table : b->d_points;
+  const size_t stride = b->d_table ? b->len : 0;
+  const int force_c = b->d_table ? b->table_c : 0;
+  switch (b->curve_id) {
+#define X(ID, DESC) case ID: msm_cached<DESC>(r, coefs, pts, len, fr_mont != 0, out_kind, force_c, stride); return 0;
+    B200_FOR_EACH_CURVE(X)
 #undef X
-    }
-    return -1;
   }
-  return ctt_b200_msm_device(b->curve_id, out_kind, r, E.d_scalars.ptr, b->d_points, len, fr_mont, 0, 0, -1);
+  return -1;
 }
 
 void ctt_b200_last_stats(ctt_b200_stats* out) {
+  static_assert(sizeof(ctt_b200_stats) == sizeof(Stats), "stats layout");
+  memcpy(out, &thread_stats(), sizeof(Stats));   // statistics of the calling thread's last MSM
+}
+
+void ctt_b200_set_concurrency(int slots) {
   Engine& E = engine();
   std::lock_guard<std::mutex> lock(E.mu);
-  static_assert(sizeof(ctt_b200_stats) == sizeof(Stats), "stats layout");
-  memcpy(out, &E.stats, sizeof(Stats));
+  engine_concurrency() = slots < 1 ? 1 : (slots > MAX_ENGINE_SLOTS ? MAX_ENGINE_SLOTS : slots);
 }
 
 void ctt_b200_set_tuning(int force_c, int reduce_chunk, int slice_len) {

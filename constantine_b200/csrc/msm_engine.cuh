@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <vector>
 #include <cuda_runtime.h>
@@ -177,9 +178,41 @@ struct Engine {
   }
 };
 
-inline Engine& engine() {
-  static Engine e;
-  return e;
+// Engine slots: slot 0 carries the process-wide settings (tuning, optional user stream) and serves the hooks; concurrent
+// MSM callers (the reference allows nested / concurrent calls, e.g. KZG batch verification issues three MSMs at once,
+// reference constantine/commitments/kzg_parallel.nim:140-172) each lease a free slot with its own streams and scratch
+// buffers, so that the latency-bound tail of one MSM overlaps the accumulate phase of another.
+constexpr int MAX_ENGINE_SLOTS = 4;
+inline Engine& engine_slot(int i) {
+  static Engine slots[MAX_ENGINE_SLOTS];
+  return slots[i];
+}
+inline Engine& engine() { return engine_slot(0); }
+inline int& engine_concurrency() {
+  static int n = 2;
+  return n;
+}
+
+struct EngineLease {
+  Engine* e;
+  std::unique_lock<std::mutex> lock;
+};
+
+inline EngineLease acquire_engine() {
+  const int n = engine_concurrency() < 1 ? 1 : (engine_concurrency() > MAX_ENGINE_SLOTS ? MAX_ENGINE_SLOTS : engine_concurrency());
+  for (int i = 0; i < n; i++) {
+    std::unique_lock<std::mutex> lk(engine_slot(i).mu, std::try_to_lock);
+    if (lk.owns_lock()) return EngineLease{&engine_slot(i), std::move(lk)};
+  }
+  static std::atomic<unsigned> rr{0};
+  int i = (int)(rr.fetch_add(1) % (unsigned)n);
+  std::unique_lock<std::mutex> lk(engine_slot(i).mu);
+  return EngineLease{&engine_slot(i), std::move(lk)};
+}
+
+inline Stats& thread_stats() {
+  static thread_local Stats s;
+  return s;
 }
 
 // ---- one MSM on device-resident inputs ------------------------------------------------------------------------
@@ -433,9 +466,10 @@ void write_result(void* r_out, const host::HXyzz<typename C::H>& p, int kind) {
 // ---- host-pointer entry (the reference's C ABI semantics): copy in, run, convert ----------------------------------
 template <class C>
 void msm_host(void* r_out, const void* coefs, const void* points, size_t len, bool fr_mont, int kind) {
-  Engine& E = engine();
-  std::lock_guard<std::mutex> lock(E.mu);
+  EngineLease lease = acquire_engine();
+  Engine& E = *lease.e;
   E.init();
+  if (&E != &engine()) E.tuning = engine().tuning;
   using HP = host::HXyzz<typename C::H>;
   if (len == 0) { write_result<C>(r_out, HP::inf(), kind); return; }  // upstream: UB; here: neutral element
   const size_t sbytes = len * 32, pbytes = len * (size_t)(2 * C::COORD_BYTES);
@@ -451,6 +485,7 @@ void msm_host(void* r_out, const void* coefs, const void* points, size_t len, bo
   B200_CUDA_CHECK(cudaEventRecord(t1, E.compute()));
   HP r = msm_device<C>(E, E.d_scalars.ptr, E.d_points.ptr, len, fr_mont, 0, 0, -1, E.ev_points_ready);
   if (E.collect_timing) cudaEventElapsedTime(&E.stats.ms_h2d, t0, t1);
+  thread_stats() = E.stats;
   write_result<C>(r_out, r, kind);
 }
 
@@ -458,11 +493,31 @@ void msm_host(void* r_out, const void* coefs, const void* points, size_t len, bo
 template <class C>
 void msm_dev_ptrs(void* r_out, const void* d_coefs, const void* d_points, size_t len, bool fr_mont, int kind, int force_c,
                   int win_begin, int win_end, size_t table_stride) {
-  Engine& E = engine();
-  std::lock_guard<std::mutex> lock(E.mu);
+  EngineLease lease = acquire_engine();
+  Engine& E = *lease.e;
   E.init();
+  if (&E != &engine()) E.tuning = engine().tuning;
   using HP = host::HXyzz<typename C::H>;
+  E.stats.ms_h2d = 0;
   HP r = msm_device<C>(E, d_coefs, d_points, len, fr_mont, force_c, win_begin, win_end, nullptr, table_stride);
+  thread_stats() = E.stats;
+  write_result<C>(r_out, r, kind);
+}
+
+// cached bases: scalars come from the host, points (or their window table) are resident; one lease covers copy + MSM
+template <class C>
+void msm_cached(void* r_out, const void* coefs, const void* d_points, size_t len, bool fr_mont, int kind, int force_c,
+                size_t table_stride) {
+  EngineLease lease = acquire_engine();
+  Engine& E = *lease.e;
+  E.init();
+  if (&E != &engine()) E.tuning = engine().tuning;
+  using HP = host::HXyzz<typename C::H>;
+  E.d_scalars.ensure(len * 32 + 16);
+  B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, len * 32, cudaMemcpyHostToDevice, E.compute()));
+  E.stats.ms_h2d = 0;
+  HP r = msm_device<C>(E, E.d_scalars.ptr, d_points, len, fr_mont, force_c, 0, -1, nullptr, table_stride);
+  thread_stats() = E.stats;
   write_result<C>(r_out, r, kind);
 }
 

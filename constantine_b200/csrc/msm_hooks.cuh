@@ -201,6 +201,7 @@ void* run_precompute_table(const void* d_points, size_t n, int c, int* W_out) {
   template void msm_host<DESC>(void*, const void*, const void*, size_t, bool, int);                               \
   template void msm_dev_ptrs<DESC>(void*, const void*, const void*, size_t, bool, int, int, int, int, size_t);    \
   template void* run_precompute_table<DESC>(const void*, size_t, int, int*);                                      \
+  template void msm_cached<DESC>(void*, const void*, const void*, size_t, bool, int, int, size_t);                \
   template int run_test_ec_op<DESC>(int, void*, const void*, const void*, size_t);                                \
   template int run_sum_partials<DESC>(int, void*, const void*, size_t);                                           \
   template int run_scalar_mul_u64<DESC>(const void*, const void*, size_t, void*);
@@ -208,6 +209,7 @@ void* run_precompute_table(const void* d_points, size_t n, int c, int* W_out) {
   extern template void msm_host<DESC>(void*, const void*, const void*, size_t, bool, int);                        \
   extern template void msm_dev_ptrs<DESC>(void*, const void*, const void*, size_t, bool, int, int, int, int, size_t); \
   extern template void* run_precompute_table<DESC>(const void*, size_t, int, int*);                               \
+  extern template void msm_cached<DESC>(void*, const void*, const void*, size_t, bool, int, int, size_t);         \
   extern template int run_test_ec_op<DESC>(int, void*, const void*, const void*, size_t);                         \
   extern template int run_sum_partials<DESC>(int, void*, const void*, size_t);                                    \
   extern template int run_scalar_mul_u64<DESC>(const void*, const void*, size_t, void*);

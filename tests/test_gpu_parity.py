@@ -262,9 +262,10 @@ def test_adversarial_distribution_large(M, lib, tp):
         assert pyref.jac_bytes_to_affine(M.multi_scalar_mul_vartime_parallel(tp, cv, scal, pts, n), cv) == want
 
 
-def test_concurrent_callers_are_serialised(M, oracle_lib):
-    """The reference allows nested / concurrent MSM calls (SURVEY.md 8b "Threading"); the engine serialises them with a
-    mutex. Four Python threads hammer the C symbol with different inputs; every result must match its own oracle value."""
+def test_concurrent_callers(M, oracle_lib):
+    """The reference allows nested / concurrent MSM calls (SURVEY.md 8b "Threading"); concurrent callers lease separate
+    engine slots (own streams and scratch) or queue on a slot's mutex. Four Python threads hammer the C symbol with
+    different inputs; every result must match its own oracle value."""
     import threading
     cv = CURVES["bn254_snarks_g1"]
     _, pool = point_pool(cv)
