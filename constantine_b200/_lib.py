@@ -48,6 +48,14 @@ def load():
     lib.ctt_b200_bases_precompute.restype = ci
     lib.ctt_b200_msm_cached_bases.argtypes = [vp, ci, vp, vp, sz, ci]
     lib.ctt_b200_msm_cached_bases.restype = ci
+    lib.ctt_b200_msm_batch_host.argtypes = [ci, ci, vp, vp, vp, sz, sz, ci, ci]
+    lib.ctt_b200_msm_batch_host.restype = ci
+    lib.ctt_b200_msm_batch_cached_bases.argtypes = [vp, ci, vp, vp, sz, sz, ci, ci]
+    lib.ctt_b200_msm_batch_cached_bases.restype = ci
+    lib.ctt_b200_bases_precompute_for.argtypes = [vp, sz, ci]
+    lib.ctt_b200_bases_precompute_for.restype = ci
+    lib.ctt_b200_sum_reduce_host.argtypes = [ci, ci, vp, vp, sz]
+    lib.ctt_b200_sum_reduce_host.restype = ci
     lib.ctt_b200_last_stats.argtypes = [ctypes.POINTER(Stats)]
     lib.ctt_b200_last_stats.restype = None
     lib.ctt_b200_set_tuning.argtypes = [ci, ci, ci]

@@ -112,9 +112,15 @@ void ctt_b200_bases_free(ctt_b200_bases* bases) {
   delete b;
 }
 
+int ctt_b200_bases_precompute_for(ctt_b200_bases* bases, size_t msm_len, int c);
 int ctt_b200_bases_precompute(ctt_b200_bases* bases, int c) {
   Bases* b = reinterpret_cast<Bases*>(bases);
-  if (!b || b->len == 0) return -1;
+  return ctt_b200_bases_precompute_for(bases, b ? b->len : 0, c);
+}
+
+int ctt_b200_bases_precompute_for(ctt_b200_bases* bases, size_t msm_len, int c) {
+  Bases* b = reinterpret_cast<Bases*>(bases);
+  if (!b || b->len == 0 || msm_len == 0) return -1;
   if (b->d_table) { cudaFree(b->d_table); b->d_table = nullptr; }
   int bits = 0;
   switch (b->curve_id) {
@@ -123,9 +129,12 @@ int ctt_b200_bases_precompute(ctt_b200_bases* bases, int c) {
 #undef X
     default: return -1;
   }
-  if (c <= 0) c = choose_window_table(b->len, bits);
+  // one MSM over all bases: its single bucket set is reduced by a latency-bound chain; a bank of small MSMs reduces
+  // many bucket sets side by side (throughput-bound), hence the lighter bucket weight
+  if (c <= 0) c = choose_window_table(msm_len, bits, b->len >= 8 * msm_len ? 80.0 : 400.0);
   if (c < 2) c = 2;
   if (c > 20) c = 20;
+  while (c < 20 && (size_t)(bits / c + 1) * b->len >= (1ull << 31)) c++;
   if ((size_t)(bits / c + 1) * b->len >= (1ull << 31)) return -2;
   switch (b->curve_id) {
 #define X(ID, DESC) case ID: b->d_table = run_precompute_table<DESC>(b->d_points, b->len, c, &b->table_W); break;
@@ -144,6 +153,41 @@ int ctt_b200_msm_cached_bases(const ctt_b200_bases* bases, int out_kind, void* r
   const int force_c = b->d_table ? b->table_c : 0;
   switch (b->curve_id) {
 #define X(ID, DESC) case ID: msm_cached<DESC>(r, coefs, pts, len, fr_mont != 0, out_kind, force_c, stride); return 0;
+    B200_FOR_EACH_CURVE(X)
+#undef X
+  }
+  return -1;
+}
+
+int ctt_b200_msm_batch_host(int curve_id, int out_kind, void* r, const void* coefs, const void* points, size_t batch,
+                            size_t len, int fr_mont, int shared_points) {
+  switch (curve_id) {
+#define X(ID, DESC) case ID: msm_batch_host<DESC>(r, coefs, points, batch, len, fr_mont != 0, out_kind, shared_points != 0); return 0;
+    B200_FOR_EACH_CURVE(X)
+#undef X
+  }
+  return -1;
+}
+
+int ctt_b200_msm_batch_cached_bases(const ctt_b200_bases* bases, int out_kind, void* r, const void* coefs, size_t batch,
+                                    size_t len, int fr_mont, int shared_points) {
+  const Bases* b = reinterpret_cast<const Bases*>(bases);
+  if (!b) return -1;
+  if ((shared_points ? len : batch * len) > b->len) return -1;
+  const void* pts = b->d_table ? b->d_table : b->d_points;
+  const size_t stride = b->d_table ? b->len : 0;
+  const int force_c = b->d_table ? b->table_c : 0;
+  switch (b->curve_id) {
+#define X(ID, DESC) case ID: msm_batch_cached<DESC>(r, coefs, pts, batch, len, fr_mont != 0, out_kind, force_c, stride, shared_points != 0); return 0;
+    B200_FOR_EACH_CURVE(X)
+#undef X
+  }
+  return -1;
+}
+
+int ctt_b200_sum_reduce_host(int curve_id, int out_kind, void* r, const void* points, size_t len) {
+  switch (curve_id) {
+#define X(ID, DESC) case ID: sum_reduce_host<DESC>(r, points, len, out_kind); return 0;
     B200_FOR_EACH_CURVE(X)
 #undef X
   }

@@ -202,6 +202,9 @@ void* run_precompute_table(const void* d_points, size_t n, int c, int* W_out) {
   template void msm_dev_ptrs<DESC>(void*, const void*, const void*, size_t, bool, int, int, int, int, size_t);    \
   template void* run_precompute_table<DESC>(const void*, size_t, int, int*);                                      \
   template void msm_cached<DESC>(void*, const void*, const void*, size_t, bool, int, int, size_t);                \
+  template void msm_batch_host<DESC>(void*, const void*, const void*, size_t, size_t, bool, int, bool);           \
+  template void msm_batch_cached<DESC>(void*, const void*, const void*, size_t, size_t, bool, int, int, size_t, bool); \
+  template void sum_reduce_host<DESC>(void*, const void*, size_t, int);                                           \
   template int run_test_ec_op<DESC>(int, void*, const void*, const void*, size_t);                                \
   template int run_sum_partials<DESC>(int, void*, const void*, size_t);                                           \
   template int run_scalar_mul_u64<DESC>(const void*, const void*, size_t, void*);
@@ -210,6 +213,9 @@ void* run_precompute_table(const void* d_points, size_t n, int c, int* W_out) {
   extern template void msm_dev_ptrs<DESC>(void*, const void*, const void*, size_t, bool, int, int, int, int, size_t); \
   extern template void* run_precompute_table<DESC>(const void*, size_t, int, int*);                               \
   extern template void msm_cached<DESC>(void*, const void*, const void*, size_t, bool, int, int, size_t);         \
+  extern template void msm_batch_host<DESC>(void*, const void*, const void*, size_t, size_t, bool, int, bool);    \
+  extern template void msm_batch_cached<DESC>(void*, const void*, const void*, size_t, size_t, bool, int, int, size_t, bool); \
+  extern template void sum_reduce_host<DESC>(void*, const void*, size_t, int);                                    \
   extern template int run_test_ec_op<DESC>(int, void*, const void*, const void*, size_t);                         \
   extern template int run_sum_partials<DESC>(int, void*, const void*, size_t);                                    \
   extern template int run_scalar_mul_u64<DESC>(const void*, const void*, size_t, void*);

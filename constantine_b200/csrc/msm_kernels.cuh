@@ -69,13 +69,17 @@ __device__ __forceinline__ void window_digit(const uint32_t* k, const DigitPlan&
 
 // One thread per scalar. FR_MONT: scalars arrive as Fr Montgomery residues and are first converted to canonical
 // integers by one Montgomery reduction (multiplication by the integer 1), like the reference's fromField pass.
-// key = w_local * key_stride + bucket  (key_stride = B normally; 0 when all windows share one bucket set because the
-// points come from a table of precomputed window multiples), val = (w_local * val_stride + i) | sign << 31
-// (val_stride = 0 normally: every window references point i; = table row length in table mode).
+// key = m * msm_key_stride + w_local * key_stride + bucket, val = (w_local * val_stride + point index) | sign << 31.
+//   single MSM:  m = 0; key_stride = B; val_stride = 0 (every window references point i)
+//   table mode:  key_stride = 0 (all windows share one bucket set because the points come from a table of precomputed
+//                window multiples), val_stride = table row length
+//   batch:       scalar i belongs to MSM m = i / per; msm_key_stride = bucket sets' size per MSM; the point index is
+//                i (every MSM has its own bases) or i - m * per (`shared`: all MSMs use the same bases)
 template <class FrParams, bool FR_MONT>
 __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ scalars, uint32_t n, DigitPlan plan,
                                                 uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                uint32_t key_stride, uint32_t no_key, uint32_t val_stride) {
+                                                uint32_t key_stride, uint32_t no_key, uint32_t val_stride,
+                                                uint32_t per, uint32_t msm_key_stride, uint32_t shared) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t k[8];
@@ -87,13 +91,16 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
     uint32_t one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
     fe_mul<FrParams>(k, k, one);
   }
+  const uint32_t m = i / per;
+  const uint32_t ref = shared ? i - m * per : i;
+  const uint32_t key_base = m * msm_key_stride;
   for (int w = plan.win_begin; w < plan.win_end; w++) {
     uint32_t val, neg;
     window_digit(k, plan, w, val, neg);
     const uint32_t wl = (uint32_t)(w - plan.win_begin);
     size_t slot = (size_t)wl * n + i;
-    keys[slot] = val ? wl * key_stride + (val - 1u) : no_key;
-    vals[slot] = (wl * val_stride + i) | (neg << 31);
+    keys[slot] = val ? key_base + wl * key_stride + (val - 1u) : no_key;
+    vals[slot] = (wl * val_stride + ref) | (neg << 31);
   }
 }
 
@@ -343,6 +350,44 @@ __global__ void __launch_bounds__(128) k_row_sum_warp(const uint32_t* in, uint32
     padd<T, INL>(acc, other);
   }
   if (lane == 0) store_xyzz(out, warp, acc);
+}
+
+// Batch tail: one thread per MSM of a batch. parts[(m * nwd + w) * row + i] are the <= 4 partial sums of window w of
+// MSM m; the thread adds them up and runs Horner over the windows (c doublings + one addition per window, reference
+// ec_multi_scalar_mul_parallel.nim:198-203). nwd = 1 (table mode) leaves just the partial sums.
+template <class T>
+__global__ void __launch_bounds__(64) k_batch_tail(const uint32_t* parts, uint32_t row, int nwd, int c, uint32_t batch, uint32_t* out) {
+  uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= batch) return;
+  Xyzz<T> r = Xyzz<T>::inf();
+#pragma unroll 1
+  for (int w = nwd - 1; w >= 0; w--) {
+    if (w != nwd - 1) {
+#pragma unroll 1
+      for (int i = 0; i < c; i++) xyzz_dbl_ni(r);
+    }
+#pragma unroll 1
+    for (uint32_t i = 0; i < row; i++) {
+      Xyzz<T> p = load_xyzz<T>(parts, ((size_t)m * nwd + w) * row + i);
+      xyzz_add_ni(r, p);
+    }
+  }
+  store_xyzz(out, m, r);
+}
+
+// Sum of affine points (reference sum_reduce_vartime, ec_shortweierstrass_batch_ops.nim:649-664): thread t adds the
+// points t, t + T, t + 2T, ... (neighbouring threads read neighbouring points); k_row_sum_warp finishes.
+template <class T>
+__global__ void __launch_bounds__(128) k_sum_strided(const uint32_t* __restrict__ points, size_t n, uint32_t* out) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  Xyzz<T> acc = Xyzz<T>::inf();
+#pragma unroll 1
+  for (size_t i = t; i < n; i += stride) {
+    Aff<T> p = load_affine<T>(points, (uint32_t)i);
+    xyzz_madd_ni(acc, p);
+  }
+  store_xyzz(out, t, acc);
 }
 
 }  // namespace b200

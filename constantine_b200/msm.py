@@ -6,6 +6,10 @@ Names follow the reference:
       ctt_<curve>_<jac|prj>_multi_scalar_mul_<big|fr>_coefs_vartime_parallel (bindings/c_curve_decls_parallel.nim:31-45)
   multi_scalar_mul_vartime           <->  reference constantine/math/elliptic/ec_multi_scalar_mul.nim:525-568 (serial twin)
   Threadpool                          <->  reference constantine/threadpool/threadpool.nim:943-1041 (new / shutdown)
+  PrecomputedMSM (init / msm_vartime) <->  reference constantine/math/elliptic/ec_multi_scalar_mul_precomp.nim:28-33, 109-161, 192-240
+  PrecomputedMSMBank                  <->  the `openArray[PrecomputedMSM]` banks of reference constantine/math/matrix/toeplitz.nim:347-360
+  sum_reduce_vartime(_parallel)       <->  reference constantine/math/elliptic/ec_shortweierstrass_batch_ops.nim:649-664,
+                                           ec_shortweierstrass_batch_ops_parallel.nim:110-123
 
 Buffers are `bytes`/`bytearray`/numpy arrays/anything exposing the buffer protocol, laid out exactly like the
 reference's C structs (see include/ctt_b200_msm.h). Results come back as `bytes` of the _jac / _prj struct.
@@ -122,12 +126,24 @@ class CachedBases:
         self.n = length if length is not None else len(memoryview(points).cast("B")) // self.curve.aff_bytes
         self._h = _lib.load().ctt_b200_bases_upload(self.curve.curve_id, _buf(points), self.n)
 
-    def precompute(self, c: int = 0) -> int:
-        """One-time table of window multiples 2^(c w) P_i (ctt_b200_bases_precompute); returns the window size used."""
-        rc = _lib.load().ctt_b200_bases_precompute(self._h, c)
+    def precompute(self, c: int = 0, msm_len: int = 0) -> int:
+        """One-time table of window multiples 2^(c w) P_i (ctt_b200_bases_precompute[_for]); returns the window size
+        used. msm_len: length of the MSMs the bases will serve when they hold a whole bank (default: all bases)."""
+        lib = _lib.load()
+        rc = lib.ctt_b200_bases_precompute_for(self._h, msm_len, c) if msm_len else lib.ctt_b200_bases_precompute(self._h, c)
         if rc < 0:
             raise ValueError("ctt_b200_bases_precompute failed")
         return rc
+
+    def msm_batch(self, coefs, batch: int, length: int, out=OUT_JAC, coef_kind="big", shared_points=False) -> list:
+        """`batch` MSMs of `length` terms in one engine pass over the cached bases (ctt_b200_msm_batch_cached_bases)."""
+        size = self.curve.coord_bytes * (4 if out == OUT_XYZZ else 3)
+        r = ctypes.create_string_buffer(max(1, size * batch))
+        rc = _lib.load().ctt_b200_msm_batch_cached_bases(self._h, out, r, _buf(coefs), batch, length, int(coef_kind == "fr"),
+                                                         int(shared_points))
+        if rc != 0:
+            raise ValueError("ctt_b200_msm_batch_cached_bases failed (batch*len exceeds the cached bases?)")
+        return [r.raw[m * size:(m + 1) * size] for m in range(batch)]
 
     def msm(self, coefs, length=None, out=OUT_JAC, coef_kind="big") -> bytes:
         n = length if length is not None else len(memoryview(coefs).cast("B")) // 32
@@ -141,6 +157,82 @@ class CachedBases:
         if self._h:
             _lib.load().ctt_b200_bases_free(self._h)
             self._h = None
+
+
+def msm_batch(curve, coefs, points, batch: int, length: int, out=OUT_JAC, coef_kind="big", shared_points=False) -> list:
+    """r[m] = sum_i coefs[m*length + i] * points[(0 if shared_points else m*length) + i] for m < batch, host buffers, one
+    engine pass (ctt_b200_msm_batch_host). Returns the list of result structs."""
+    cv = _curve(curve)
+    size = cv.coord_bytes * (4 if out == OUT_XYZZ else 3)
+    r = ctypes.create_string_buffer(max(1, size * batch))
+    rc = _lib.load().ctt_b200_msm_batch_host(cv.curve_id, out, r, _buf(coefs), _buf(points), batch, length, int(coef_kind == "fr"),
+                                             int(shared_points))
+    if rc != 0:
+        raise ValueError("ctt_b200_msm_batch_host: bad curve id")
+    return [r.raw[m * size:(m + 1) * size] for m in range(batch)]
+
+
+class PrecomputedMSM:
+    """Fixed-base MSM context, the reference's `PrecomputedMSM[EC, N]`.
+
+    reference: `ctx.init(basis, t, b)` builds comb tables (stride t, window b) on the host and `ctx.msm_vartime(r, scalars)`
+    walks them with mixed additions. Here `init` uploads the basis and builds the table 2^(c w) P_i in HBM and
+    `msm_vartime` is one engine pass with a single bucket set. (t, b) are accepted for source compatibility; they
+    parametrise the reference's table shape, not the result -- the window c plays their role and is chosen by the
+    engine unless given.
+    """
+
+    def __init__(self):
+        self._bases = None
+        self.N = 0
+
+    def init(self, curve, basis, t: int = 0, b: int = 0, c: int = 0):
+        self._bases = CachedBases(curve, basis)
+        self.N = self._bases.n
+        self.c = self._bases.precompute(c)
+        return self
+
+    def msm_vartime(self, scalars, out="jac", coef_kind="big") -> bytes:
+        n = len(memoryview(scalars).cast("B")) // 32
+        if n != self.N:
+            raise ValueError("PrecomputedMSM.msm_vartime: need exactly N scalars")     # reference: openArray of length N
+        return self._bases.msm(scalars, n, OUT_JAC if out == "jac" else OUT_PRJ, coef_kind)
+
+    def free(self):
+        if self._bases:
+            self._bases.free()
+            self._bases = None
+
+
+class PrecomputedMSMBank:
+    """`count` PrecomputedMSM objects of N points each, evaluated together (the reference loops over the bank,
+    matrix/toeplitz.nim:357-360: `polyphaseSpectrumBank[i].msm_vartime(output[i], scalars_i)`)."""
+
+    def __init__(self, curve, bases, count: int, n: int, c: int = 0):
+        self.count, self.N = count, n
+        self._bases = CachedBases(curve, bases, count * n)
+        self.c = self._bases.precompute(c, msm_len=n)
+
+    def msm_vartime(self, scalars, out="jac", coef_kind="big") -> list:
+        return self._bases.msm_batch(scalars, self.count, self.N, OUT_JAC if out == "jac" else OUT_PRJ, coef_kind)
+
+    def free(self):
+        self._bases.free()
+
+
+def sum_reduce_vartime(curve, points, length=None, out="jac") -> bytes:
+    """r = P_0 + ... + P_{n-1} (ctt_b200_sum_reduce_host)."""
+    cv = _curve(curve)
+    n = length if length is not None else len(memoryview(points).cast("B")) // cv.aff_bytes
+    r = ctypes.create_string_buffer(cv.jac_bytes)
+    rc = _lib.load().ctt_b200_sum_reduce_host(cv.curve_id, OUT_JAC if out == "jac" else OUT_PRJ, r, _buf(points), n)
+    if rc != 0:
+        raise ValueError("ctt_b200_sum_reduce_host: bad curve id")
+    return r.raw
+
+
+def sum_reduce_vartime_parallel(tp, curve, points, length=None, out="jac") -> bytes:
+    return sum_reduce_vartime(curve, points, length, out)
 
 
 EVM_STATUS = ("cttEVM_Success", "cttEVM_InvalidInputSize", "cttEVM_InvalidOutputSize", "cttEVM_IntLargerThanModulus",
