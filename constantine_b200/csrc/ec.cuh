@@ -211,6 +211,49 @@ B200_DEV void xyzz_add(Xyzz<T>& acc, const Xyzz<T>& q) {
   acc.zzz = acc.zzz * q.zzz * PPP;
 }
 
+// Fully unrolled multipliers (mul_u / sqr_u) for single chains of dependent point operations, where nothing hides the
+// latency of the rolled-loop multiplier (k_batch_tail: one thread per MSM runs Horner over its windows).
+template <class T>
+B200_DEV Xyzz<T> xyzz_dbl_u(const Xyzz<T>& p) {
+  T U = p.y.dbl();
+  T V = U.sqr_u();
+  T W = U.mul_u(V);
+  T S = p.x.mul_u(V);
+  T X2 = p.x.sqr_u();
+  T M = X2.dbl() + X2;
+  Xyzz<T> r;
+  r.x = M.sqr_u() - S.dbl();
+  r.y = M.mul_u(S - r.x) - W.mul_u(p.y);
+  r.zz = V.mul_u(p.zz);
+  r.zzz = W.mul_u(p.zzz);
+  return r;
+}
+template <class T>
+B200_DEV void xyzz_add_u(Xyzz<T>& acc, const Xyzz<T>& q) {
+  if (q.is_inf()) return;
+  if (acc.is_inf()) { acc = q; return; }
+  T U1 = acc.x.mul_u(q.zz);
+  T U2 = q.x.mul_u(acc.zz);
+  T S1 = acc.y.mul_u(q.zzz);
+  T S2 = q.y.mul_u(acc.zzz);
+  T P = U2 - U1;
+  T R = S2 - S1;
+  if (P.is_zero()) {
+    if (R.is_zero()) xyzz_dbl_ni(acc);
+    else acc = Xyzz<T>::inf();
+    return;
+  }
+  T PP = P.sqr_u();
+  T PPP = P.mul_u(PP);
+  T Q = U1.mul_u(PP);
+  T X3 = R.sqr_u() - PPP - Q.dbl();
+  T Y3 = R.mul_u(Q - X3) - S1.mul_u(PPP);
+  acc.x = X3;
+  acc.y = Y3;
+  acc.zz = acc.zz.mul_u(q.zz).mul_u(PP);
+  acc.zzz = acc.zzz.mul_u(q.zzz).mul_u(PPP);
+}
+
 template <class T>
 __device__ __noinline__ void xyzz_add_ni(Xyzz<T>& acc, const Xyzz<T>& q) { xyzz_add(acc, q); }
 template <class T>

@@ -206,14 +206,13 @@ void ctt_b200_set_concurrency(int slots) {
 }
 
 void ctt_b200_set_tuning(int force_c, int reduce_chunk, int slice_len) {
-  const int sum_group = slice_len;
   Engine& E = engine();
   std::lock_guard<std::mutex> lock(E.mu);
   if (force_c > 0) E.tuning.force_c = force_c;
   if (force_c < 0) E.tuning.force_c = 0;
   if (reduce_chunk > 0) E.tuning.reduce_chunk = reduce_chunk;
-  if (sum_group > 0) E.tuning.slice_len = sum_group;
-  if (sum_group < 0) E.tuning.slice_len = 0;
+  if (slice_len > 0) E.tuning.slice_len = slice_len;
+  if (slice_len < 0) E.tuning.slice_len = 0;
 }
 
 void ctt_b200_set_groups(int groups) {

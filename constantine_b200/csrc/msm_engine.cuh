@@ -652,7 +652,8 @@ void sum_reduce_host(void* r_out, const void* points, size_t len, int kind) {
   while (row > 4) {
     uint32_t out_row = (row + 31) / 32;
     dim3 blk(128), grd((unsigned)(((size_t)out_row * 32 + 127) / 128));
-    k_row_sum_warp<T, false><<<grd, blk, 0, s>>>((const uint32_t*)(in_a ? E.red_a.ptr : E.red_b.ptr), row, out_row, 1,
+    // same instantiation as the engine's reduce phase (point additions inline for single-field coordinates)
+    k_row_sum_warp<T, (T::WORDS <= B200_INLINE_MAX_WORDS)><<<grd, blk, 0, s>>>((const uint32_t*)(in_a ? E.red_a.ptr : E.red_b.ptr), row, out_row, 1,
                                                  (uint32_t*)(in_a ? E.red_b.ptr : E.red_a.ptr));
     row = out_row;
     in_a = !in_a;

@@ -357,6 +357,7 @@ __global__ void __launch_bounds__(128) k_row_sum_warp(const uint32_t* in, uint32
 // ec_multi_scalar_mul_parallel.nim:198-203). nwd = 1 (table mode) leaves just the partial sums.
 template <class T>
 __global__ void __launch_bounds__(64) k_batch_tail(const uint32_t* parts, uint32_t row, int nwd, int c, uint32_t batch, uint32_t* out) {
+  constexpr bool FAST = T::WORDS <= 12;   // single-field coordinates: unrolled multipliers inline (latency); Fp2: out of line
   uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= batch) return;
   Xyzz<T> r = Xyzz<T>::inf();
@@ -364,12 +365,14 @@ __global__ void __launch_bounds__(64) k_batch_tail(const uint32_t* parts, uint32
   for (int w = nwd - 1; w >= 0; w--) {
     if (w != nwd - 1) {
 #pragma unroll 1
-      for (int i = 0; i < c; i++) xyzz_dbl_ni(r);
+      for (int i = 0; i < c; i++) {
+        if constexpr (FAST) r = xyzz_dbl_u(r); else xyzz_dbl_ni(r);
+      }
     }
 #pragma unroll 1
     for (uint32_t i = 0; i < row; i++) {
       Xyzz<T> p = load_xyzz<T>(parts, ((size_t)m * nwd + w) * row + i);
-      xyzz_add_ni(r, p);
+      if constexpr (FAST) xyzz_add_u(r, p); else xyzz_add_ni(r, p);
     }
   }
   store_xyzz(out, m, r);
