@@ -412,7 +412,9 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
       launches += 2;
       uint32_t row = chunks;
       bool in_a = true;
-      while (row > 4) {
+      // single MSM: <= 4 partial sums per window go to the host tail; batch: down to one, the device tail is a serial chain
+      const uint32_t row_stop = batch > 1 ? 1u : 4u;
+      while (row > row_stop) {
         uint32_t out_row = (row + 31) / 32;
         size_t warps = (size_t)out_row * nwg;
         dim3 blk(128), grd((unsigned)((warps * 32 + 127) / 128));
