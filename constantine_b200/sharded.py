@@ -9,6 +9,9 @@ the host of every rank. An elliptic-curve addition is not an NCCL reduction op, 
 
 Window sharding (north star) is the alternative when every rank already holds all N pairs: rank g owns a contiguous
 range of windows and returns sum_{w in range} 2^(c w) S_w; the combination step is identical.
+
+A bank of independent MSMs (msm.msm_batch / PrecomputedMSMBank) shards by member: rank g evaluates members
+balanced_chunk(batch, world, g) in one engine pass; the only exchange is the all_gather of the result structs.
 """
 import ctypes
 from typing import Callable, Optional, Tuple
@@ -88,3 +91,30 @@ def msm_sharded_device(curve, d_coefs: int, d_points: int, n_local: int, group=N
     else:
         part = local_msm(cv, d_coefs, d_points, n_local)
     return msm_point_sharded(cv, part, group=group, device=device, out=out)
+
+
+def msm_batch_sharded(curve, coefs, points, batch: int, length: int, group=None, device=None, out=_msm.OUT_JAC,
+                      coef_kind="big", shared_points=False, local_batch: Optional[Callable] = None) -> list:
+    """`batch` independent MSMs of `length` terms split by member over the ranks of `group`; every rank returns all
+    `batch` results. coefs / points are the full host buffers (each rank reads only its members' slices).
+    `local_batch(curve, coefs, points, members, length)` lets the CPU tests substitute the engine call."""
+    import torch.distributed as dist
+    cv = curve if isinstance(curve, CurveParams) else CURVES[curve]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = balanced_chunk(batch, world, rank)
+    cmv, pmv = memoryview(coefs).cast("B"), memoryview(points).cast("B")
+    c_loc = cmv[lo * length * 32:hi * length * 32]
+    p_loc = pmv if shared_points else pmv[lo * length * cv.aff_bytes:hi * length * cv.aff_bytes]
+    if local_batch is None:
+        res = _msm.msm_batch(cv, c_loc, p_loc, hi - lo, length, out=out, coef_kind=coef_kind, shared_points=shared_points)
+    else:
+        res = local_batch(cv, c_loc, p_loc, hi - lo, length)
+    size = cv.coord_bytes * (4 if out == _msm.OUT_XYZZ else 3)
+    per = -(-batch // world)                        # members per rank, rounded up: fixed-size payload for the all_gather
+    payload = b"".join(res) + bytes(size * (per - (hi - lo)))
+    parts = _all_gather_bytes(payload, group=group, device=device)
+    out_list = []
+    for g in range(world):
+        glo, ghi = balanced_chunk(batch, world, g)
+        out_list += [parts[g][i * size:(i + 1) * size] for i in range(ghi - glo)]
+    return out_list

@@ -45,6 +45,21 @@ def _worker(rank, world, port, mode, q):
                 return affine_to_xyzz_bytes(aff, cvv)
 
             got = sharded.msm_sharded_device(cv, 0, 0, hi - lo, local_msm=local)
+        elif mode == "bank":   # a bank of 5 MSMs x 9 terms split by member (3 + 2); every rank ends with all 5 results
+            batch, m = 5, 9
+            bks = [rnd.getrandbits(255) for _ in range(batch * m)]
+            bpts = [pool[rnd.randrange(len(pool))] for _ in range(batch * m)]
+            cb, pb = pack(cv, bks, bpts)
+
+            def local_batch(cvv, c_loc, p_loc, members, length):  # stands in for ctt_b200_msm_batch_host
+                return [oracle.msm(cvv, bytes(c_loc[i * length * 32:(i + 1) * length * 32]),
+                                   bytes(p_loc[i * length * cvv.aff_bytes:(i + 1) * length * cvv.aff_bytes]), length)
+                        for i in range(members)]
+
+            res = sharded.msm_batch_sharded(cv, cb, pb, batch, m, local_batch=local_batch)
+            wants = [pyref.msm_naive_fast(bks[i * m:(i + 1) * m], bpts[i * m:(i + 1) * m], cv) for i in range(batch)]
+            q.put((rank, [pyref.jac_bytes_to_affine(r, cv) for r in res] == wants))
+            return
         else:  # window sharding: every rank holds all pairs, owns a window range, returns sum 2^(cw) S_w over its range
             c = 8
             W = 255 // c + 1
@@ -66,7 +81,7 @@ def _worker(rank, world, port, mode, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["points", "windows"])
+@pytest.mark.parametrize("mode", ["points", "windows", "bank"])
 def test_two_rank_sharded_msm(mode):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
