@@ -170,7 +170,11 @@ B200_DEV void xyzz_madd(Xyzz<T>& acc, const Aff<T>& q) {
   T PPP = P.mul_u(PP);
   T Q = acc.x.mul_u(PP);
   T X3 = R.sqr_u() - PPP - Q.dbl();
+#if defined(B200_MADD_ROLLED) || defined(B200_NO_DOT2)
   T Y3 = R.mul_u(Q - X3) - acc.y.mul_u(PPP);
+#else
+  T Y3 = T::dot2_u(R, Q - X3, acc.y.neg(), PPP);   // R (Q - X3) - Y1 PPP with one Montgomery reduction
+#endif
   acc.x = X3;
   acc.y = Y3;
   acc.zz = acc.zz.mul_u(PP);

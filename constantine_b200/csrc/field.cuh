@@ -194,6 +194,97 @@ B200_DEV void fe_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   for (int k = 0; k < N; k++) r[k] = t[k];
 }
 
+// (E,O) += c * di  -- a second product row on top of a step's first one (same even/odd carry chains as mont_step).
+// No chain can carry out of its top limb: the running value stays below 2^(32(N+1)) (see fe_dot2).
+template <class F>
+B200_DEV void add_product_row(uint32_t* E, uint32_t* O, const uint32_t* c, uint32_t di) {
+  constexpr int N = F::N;
+  O[0] = p_mad_lo_cc(c[1], di, O[0]);
+  O[1] = p_madc_hi_cc(c[1], di, O[1]);
+#pragma unroll
+  for (int j = 2; j < N - 2; j += 2) {
+    O[j] = p_madc_lo_cc(c[j + 1], di, O[j]);
+    O[j + 1] = p_madc_hi_cc(c[j + 1], di, O[j + 1]);
+  }
+  O[N - 2] = p_madc_lo_cc(c[N - 1], di, O[N - 2]);
+  O[N - 1] = p_madc_hi(c[N - 1], di, O[N - 1]);
+  E[0] = p_mad_lo_cc(c[0], di, E[0]);
+  E[1] = p_madc_hi_cc(c[0], di, E[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    E[j] = p_madc_lo_cc(c[j], di, E[j]);
+    E[j + 1] = p_madc_hi_cc(c[j], di, E[j + 1]);
+  }
+  O[N - 1] = p_addc(O[N - 1], 0);
+}
+
+// Outer iteration of the two-product form: same as mont_step up to the reduction round, with the second row in between.
+template <class F>
+B200_DEV void mont_step2(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, const uint32_t* c, uint32_t di) {
+  constexpr int N = F::N;
+  E[0] = p_add_cc(E[0], O[1]);
+#pragma unroll
+  for (int j = 0; j < N - 2; j += 2) {
+    O[j] = p_madc_lo_cc(a[j + 1], bi, O[j + 2]);
+    O[j + 1] = p_madc_hi_cc(a[j + 1], bi, O[j + 3]);
+  }
+  O[N - 2] = p_madc_lo_cc(a[N - 1], bi, 0);
+  O[N - 1] = p_madc_hi(a[N - 1], bi, 0);
+  E[0] = p_mad_lo_cc(a[0], bi, E[0]);
+  E[1] = p_madc_hi_cc(a[0], bi, E[1]);
+#pragma unroll
+  for (int j = 2; j < N; j += 2) {
+    E[j] = p_madc_lo_cc(a[j], bi, E[j]);
+    E[j + 1] = p_madc_hi_cc(a[j], bi, E[j + 1]);
+  }
+  O[N - 1] = p_addc(O[N - 1], 0);
+  add_product_row<F>(E, O, c, di);
+  mont_round<F>(E, O);
+}
+
+// 3p < 2^(32N)  (sufficient test on the top limb)
+template <class F>
+__host__ __device__ constexpr bool dot2_fits() { return 3ull * ((unsigned long long)F::P(F::N - 1) + 1ull) <= (1ull << 32); }
+
+// r = (a*b + c*d) * R^-1 mod p, canonical: ONE interleaved Montgomery reduction for two products -- 3N^2 + N
+// multiply-accumulates instead of 2(2N^2 + N). Per outer step T <- (T + a*b_i + c*d_i + m*p) / 2^32, so T < 3p
+// throughout (inputs < p), which fits N limbs for every field here (3p < 2^(32N): BLS12-381 0.31, BN254 0.57,
+// Pasta 0.75 of 2^(32N)) and the value before each division stays below 2^(32(N+1)). Two conditional subtractions finish.
+template <class F>
+B200_DEV void fe_dot2(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d) {
+  constexpr int N = F::N;
+  static_assert(N % 2 == 0 && N >= 4, "even limb count");
+  static_assert(dot2_fits<F>(), "fe_dot2 needs 3p < 2^(32N)");
+  uint32_t A[N], B[N];
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+    A[j] = p_mul_lo(a[j], b[0]);
+    A[j + 1] = p_mul_hi(a[j], b[0]);
+    B[j] = p_mul_lo(a[j + 1], b[0]);
+    B[j + 1] = p_mul_hi(a[j + 1], b[0]);
+  }
+  add_product_row<F>(A, B, c, d[0]);
+  mont_round<F>(A, B);
+#pragma unroll
+  for (int i = 1; i < N; i++) {
+    if (i & 1)
+      mont_step2<F>(B, A, a, b[i], c, d[i]);
+    else
+      mont_step2<F>(A, B, a, b[i], c, d[i]);
+  }
+  uint32_t* E = ((N - 1) & 1) ? B : A;
+  uint32_t* O = ((N - 1) & 1) ? A : B;
+  uint32_t t[N];
+  t[0] = p_add_cc(O[0], E[1]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) t[k] = p_addc_cc(O[k], E[k + 1]);
+  t[N - 1] = p_addc(O[N - 1], 0);
+  final_sub<F>(t);
+  final_sub<F>(t);
+#pragma unroll
+  for (int k = 0; k < N; k++) r[k] = t[k];
+}
+
 // Same multiplication with the outer loop kept ROLLED (two CIOS steps per iteration, the multiplier limbs rotated through
 // registers so every index stays static): one third of the code of the fully unrolled form. Experiment for the
 // instruction-fetch stalls ncu shows in k_accumulate (profiles/ncu_k_accumulate_r1.txt); selected with -DB200_ROLLED_MUL.
@@ -312,6 +403,11 @@ struct Fp {
   // fully unrolled multiplier regardless of the policy above (the hot mixed add of k_accumulate is faster with it)
   B200_DEV Fp mul_u(const Fp& b) const { Fp r; fe_mul<F>(r.l, l, b.l); return r; }
   B200_DEV Fp sqr_u() const { Fp r; fe_mul<F>(r.l, l, l); return r; }
+  // a*b + c*d with one reduction (unrolled)
+  static B200_DEV Fp dot2_u(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+    if constexpr (dot2_fits<F>()) { Fp r; fe_dot2<F>(r.l, a.l, b.l, c.l, d.l); return r; }
+    else return a.mul_u(b) + c.mul_u(d);   // fields without the headroom (BLS12-381 Fr): two reductions
+  }
   B200_DEV Fp neg() const { Fp r; fe_neg<F>(r.l, l); return r; }
   B200_DEV Fp dbl() const { Fp r; fe_add<F>(r.l, l, l); return r; }
   // this = cond ? -this : this
@@ -392,6 +488,8 @@ struct Fp2 {
     r.c1 = t + t;
     return r;
   }
+  // a*b + c*d: no fused form here (a Karatsuba product is already cheaper than two fused pairs)
+  static B200_DEV Fp2 dot2_u(const Fp2& a, const Fp2& b, const Fp2& c, const Fp2& d) { return a.mul_u(b) + c.mul_u(d); }
   B200_DEV Fp2 neg() const { Fp2 r; r.c0 = c0.neg(); r.c1 = c1.neg(); return r; }
   B200_DEV Fp2 dbl() const { Fp2 r; r.c0 = c0.dbl(); r.c1 = c1.dbl(); return r; }
   B200_DEV void cneg(bool cond) { c0.cneg(cond); c1.cneg(cond); }

@@ -18,6 +18,7 @@ __global__ void k_test_field_op(int op, uint32_t* r, const uint32_t* a, const ui
     case 1: z = x + y; break;
     case 2: z = x - y; break;
     case 3: z = x.neg(); break;
+    case 5: z = T::dot2_u(x, y, x + y, x - y); break;   // x y + (x + y)(x - y), one reduction
     default: z = x.dbl(); break;
   }
   store_words(r + i * T::WORDS, z);

@@ -62,6 +62,12 @@ def test_field_kernels_vs_oracle(lib, oracle_lib):
             assert lib.ctt_b200_test_field_op(fid, op, out, ab, bb, cnt) == 0
             want = oracle_lib.fp_op(f, op if op < 4 else 1, ab, bb if op < 4 else ab, cnt)
             assert out.raw == want, (name, op)
+        # op 5: a b + (a + b)(a - b) through the two-product multiplier (one Montgomery reduction for both products)
+        out = ctypes.create_string_buffer(len(ab))
+        assert lib.ctt_b200_test_field_op(fid, 5, out, ab, bb, cnt) == 0
+        t1 = oracle_lib.fp_op(f, 0, ab, bb, cnt)
+        t2 = oracle_lib.fp_op(f, 0, oracle_lib.fp_op(f, 1, ab, bb, cnt), oracle_lib.fp_op(f, 2, ab, bb, cnt), cnt)
+        assert out.raw == oracle_lib.fp_op(f, 1, t1, t2, cnt), (name, "dot2")
 
 
 @pytest.mark.parametrize("curve", list(CURVES))
