@@ -285,6 +285,97 @@ B200_DEV void fe_dot2(uint32_t* r, const uint32_t* a, const uint32_t* b, const u
   for (int k = 0; k < N; k++) r[k] = t[k];
 }
 
+// r = a^2 * R^-1 mod p, canonical. Separate-operand-scanning squaring: the N(N-1)/2 off-diagonal products are computed
+// once and doubled, the N diagonal squares ride on one carry chain, then N reduction rounds: N(N-1)/2 + N + N^2
+// 32x32->64 multiply-accumulates (222 for N = 12) against 2N^2 (288) for the general product.
+// Carry discipline (every chain is a run of consecutive limb positions, exactly like the rows of fe_mul):
+//   * rows a_i * a_j with j - i odd accumulate in X, with j - i even in Y; a row's carry-out lands on the limb just above
+//     its end, which earlier rows (ending no higher) have only ever loaded with carries;
+//   * reduction round i adds m*p at positions i..i+N in two chains (even / odd limbs of p); their carry-outs belong to
+//     positions >= N and are parked in the side words C (each <= 2) instead of rippling through T.
+template <class F>
+B200_DEV void fe_sqr(uint32_t* r, const uint32_t* a) {
+  constexpr int N = F::N;
+  static_assert(N % 2 == 0 && N >= 4, "even limb count");
+  uint32_t X[2 * N], Y[2 * N];
+#pragma unroll
+  for (int k = 0; k < 2 * N; k++) { X[k] = 0; Y[k] = 0; }
+#pragma unroll
+  for (int i = 0; i < N - 1; i++) {
+    // j = i+1, i+3, ...  -> X
+    {
+#pragma unroll
+      for (int j = i + 1; j < N; j += 2) {
+        X[i + j] = (j == i + 1) ? p_mad_lo_cc(a[i], a[j], X[i + j]) : p_madc_lo_cc(a[i], a[j], X[i + j]);
+        X[i + j + 1] = p_madc_hi_cc(a[i], a[j], X[i + j + 1]);
+      }
+      const int jl = i + 1 + 2 * ((N - 1 - (i + 1)) / 2);   // last j of this class
+      X[i + jl + 2] = p_addc(X[i + jl + 2], 0);
+    }
+    // j = i+2, i+4, ...  -> Y
+    if (i + 2 < N) {
+#pragma unroll
+      for (int j = i + 2; j < N; j += 2) {
+        Y[i + j] = (j == i + 2) ? p_mad_lo_cc(a[i], a[j], Y[i + j]) : p_madc_lo_cc(a[i], a[j], Y[i + j]);
+        Y[i + j + 1] = p_madc_hi_cc(a[i], a[j], Y[i + j + 1]);
+      }
+      const int jl = i + 2 + 2 * ((N - 1 - (i + 2)) / 2);
+      Y[i + jl + 2] = p_addc(Y[i + jl + 2], 0);
+    }
+  }
+  // T = 2 (X + Y) + sum_i a_i^2 2^(64 i)
+  uint32_t T[2 * N];
+  T[0] = p_add_cc(X[0], Y[0]);
+#pragma unroll
+  for (int k = 1; k < 2 * N - 1; k++) T[k] = p_addc_cc(X[k], Y[k]);
+  T[2 * N - 1] = p_addc(X[2 * N - 1], Y[2 * N - 1]);
+  T[0] = p_add_cc(T[0], T[0]);
+#pragma unroll
+  for (int k = 1; k < 2 * N - 1; k++) T[k] = p_addc_cc(T[k], T[k]);
+  T[2 * N - 1] = p_addc(T[2 * N - 1], T[2 * N - 1]);
+  T[0] = p_mad_lo_cc(a[0], a[0], T[0]);
+  T[1] = p_madc_hi_cc(a[0], a[0], T[1]);
+#pragma unroll
+  for (int i = 1; i < N - 1; i++) {
+    T[2 * i] = p_madc_lo_cc(a[i], a[i], T[2 * i]);
+    T[2 * i + 1] = p_madc_hi_cc(a[i], a[i], T[2 * i + 1]);
+  }
+  T[2 * N - 2] = p_madc_lo_cc(a[N - 1], a[N - 1], T[2 * N - 2]);
+  T[2 * N - 1] = p_madc_hi(a[N - 1], a[N - 1], T[2 * N - 1]);
+  // N reduction rounds
+  uint32_t C[N + 1];
+#pragma unroll
+  for (int k = 0; k <= N; k++) C[k] = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const uint32_t m = T[i] * F::INV;
+    T[i] = p_mad_lo_cc(m, F::P(0), T[i]);
+    T[i + 1] = p_madc_hi_cc(m, F::P(0), T[i + 1]);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      T[i + j] = p_madc_lo_cc(m, F::P(j), T[i + j]);
+      T[i + j + 1] = p_madc_hi_cc(m, F::P(j), T[i + j + 1]);
+    }
+    C[i] = p_addc(C[i], 0);
+    T[i + 1] = p_mad_lo_cc(m, F::P(1), T[i + 1]);
+    T[i + 2] = p_madc_hi_cc(m, F::P(1), T[i + 2]);
+#pragma unroll
+    for (int j = 3; j < N; j += 2) {
+      T[i + j] = p_madc_lo_cc(m, F::P(j), T[i + j]);
+      T[i + j + 1] = p_madc_hi_cc(m, F::P(j), T[i + j + 1]);
+    }
+    C[i + 1] = p_addc(C[i + 1], 0);
+  }
+  uint32_t t[N];
+  t[0] = p_add_cc(T[N], C[0]);
+#pragma unroll
+  for (int k = 1; k < N - 1; k++) t[k] = p_addc_cc(T[N + k], C[k]);
+  t[N - 1] = p_addc(T[2 * N - 1], C[N - 1]);
+  final_sub<F>(t);
+#pragma unroll
+  for (int k = 0; k < N; k++) r[k] = t[k];
+}
+
 // Same multiplication with the outer loop kept ROLLED (two CIOS steps per iteration, the multiplier limbs rotated through
 // registers so every index stays static): one third of the code of the fully unrolled form. Experiment for the
 // instruction-fetch stalls ncu shows in k_accumulate (profiles/ncu_k_accumulate_r1.txt); selected with -DB200_ROLLED_MUL.
@@ -402,7 +493,11 @@ struct Fp {
   B200_DEV Fp sqr() const { return (*this) * (*this); }
   // fully unrolled multiplier regardless of the policy above (the hot mixed add of k_accumulate is faster with it)
   B200_DEV Fp mul_u(const Fp& b) const { Fp r; fe_mul<F>(r.l, l, b.l); return r; }
+#ifdef B200_NO_SQR
   B200_DEV Fp sqr_u() const { Fp r; fe_mul<F>(r.l, l, l); return r; }
+#else
+  B200_DEV Fp sqr_u() const { Fp r; fe_sqr<F>(r.l, l); return r; }
+#endif
   // a*b + c*d with one reduction (unrolled)
   static B200_DEV Fp dot2_u(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
     if constexpr (dot2_fits<F>()) { Fp r; fe_dot2<F>(r.l, a.l, b.l, c.l, d.l); return r; }

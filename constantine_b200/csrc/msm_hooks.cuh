@@ -19,6 +19,7 @@ __global__ void k_test_field_op(int op, uint32_t* r, const uint32_t* a, const ui
     case 2: z = x - y; break;
     case 3: z = x.neg(); break;
     case 5: z = T::dot2_u(x, y, x + y, x - y); break;   // x y + (x + y)(x - y), one reduction
+    case 6: z = x.sqr_u() + y.sqr_u(); break;           // dedicated squaring
     default: z = x.dbl(); break;
   }
   store_words(r + i * T::WORDS, z);

@@ -68,6 +68,10 @@ def test_field_kernels_vs_oracle(lib, oracle_lib):
         t1 = oracle_lib.fp_op(f, 0, ab, bb, cnt)
         t2 = oracle_lib.fp_op(f, 0, oracle_lib.fp_op(f, 1, ab, bb, cnt), oracle_lib.fp_op(f, 2, ab, bb, cnt), cnt)
         assert out.raw == oracle_lib.fp_op(f, 1, t1, t2, cnt), (name, "dot2")
+        # op 6: a^2 + b^2 through the dedicated squaring
+        out = ctypes.create_string_buffer(len(ab))
+        assert lib.ctt_b200_test_field_op(fid, 6, out, ab, bb, cnt) == 0
+        assert out.raw == oracle_lib.fp_op(f, 1, oracle_lib.fp_op(f, 0, ab, ab, cnt), oracle_lib.fp_op(f, 0, bb, bb, cnt), cnt), (name, "sqr")
 
 
 @pytest.mark.parametrize("curve", list(CURVES))
