@@ -74,3 +74,26 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_specialised_multipliers_carry_chains(rng):
+    """fe_dot2 / fe_sqr of csrc/field.cuh, emulated instruction by instruction (tests/carry_chain_emulation.py): exact
+    results on edge and random operands and no dropped carry, for every base field the mixed add runs over."""
+    import carry_chain_emulation as emu
+    from constantine_b200.curves import FIELDS
+    for name in ("bls12_381_fp", "bn254_snarks_fp", "pallas_fp", "vesta_fp"):
+        f = FIELDS[name]
+        p, n = f.modulus, f.nbytes // 4
+        R = 1 << (32 * n)
+        assert 3 * p < R, name                      # the headroom fe_dot2's static_assert demands
+        rinv = pow(R, -1, p)
+        edge = [0, 1, p - 1, p - 2, (1 << (f.bits - 1)) % p, R % p, (R - 1) % p]
+        quads = [(a, b, c, d) for a in edge for b in edge[:4] for c in (p - 1, 0) for d in (p - 1, 1)]
+        quads += [tuple(rng.randrange(p) for _ in range(4)) for _ in range(300)]
+        for a, b, c, d in quads:
+            got, _ = emu.fe_dot2(p, n, a, b, c, d)
+            assert got == (a * b + c * d) * rinv % p, (name, a, b, c, d)
+        for a in edge + [rng.randrange(p) for _ in range(300)]:
+            got, macs = emu.fe_sqr(p, n, a)
+            assert got == a * a * rinv % p, (name, a)
+            assert macs == n * (n - 1) // 2 + n + n * n        # 222 for 12 limbs, against 2 n^2 = 288 for fe_mul
