@@ -97,3 +97,17 @@ def test_specialised_multipliers_carry_chains(rng):
             got, macs = emu.fe_sqr(p, n, a)
             assert got == a * a * rinv % p, (name, a)
             assert macs == n * (n - 1) // 2 + n + n * n        # 222 for 12 limbs, against 2 n^2 = 288 for fe_mul
+
+
+def test_batched_affine_schedule_prototype():
+    """tools/proto_batched_affine.py: the in-place pairing schedule + shared inversion planned for the accumulate phase
+     gives exact bucket sums, with infinities, P + P and P - P inside the batches."""
+    import importlib.util
+    import os
+    from helpers import ROOT
+    spec = importlib.util.spec_from_file_location("proto_batched_affine", os.path.join(ROOT, "tools", "proto_batched_affine.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for curve, seed in (("bn254_snarks_g1", 1), ("bls12_381_g2", 2)):
+        adds, survivors, n = mod.self_check(curve, n=400, nbuckets=17, seed=seed)
+        assert adds > n // 2 and survivors < n // 4
