@@ -64,6 +64,8 @@ def load():
     lib.ctt_b200_set_concurrency.restype = None
     lib.ctt_b200_set_groups.argtypes = [ci]
     lib.ctt_b200_set_groups.restype = None
+    lib.ctt_b200_set_affine_levels.argtypes = [ci]
+    lib.ctt_b200_set_affine_levels.restype = None
     lib.ctt_b200_set_stream.argtypes = [vp]
     lib.ctt_b200_set_stream.restype = None
     lib.ctt_b200_sm_count.argtypes = []

@@ -221,6 +221,12 @@ void ctt_b200_set_groups(int groups) {
   E.tuning.groups = groups < 0 ? 0 : groups;
 }
 
+void ctt_b200_set_affine_levels(int levels) {
+  Engine& E = engine();
+  std::lock_guard<std::mutex> lock(E.mu);
+  E.tuning.affine_levels = levels < 0 ? 0 : (levels > 6 ? 6 : levels);
+}
+
 void ctt_b200_set_stream(void* cuda_stream) {
   Engine& E = engine();
   std::lock_guard<std::mutex> lock(E.mu);

@@ -10,6 +10,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include "msm_kernels.cuh"
 #include "host_field.hpp"
 
@@ -58,6 +59,7 @@ struct Tuning {
   int reduce_chunk = 16;      // L: buckets per bucket-reduce thread
   int slice_len = 0;          // K: sorted entries per accumulate thread (0 = automatic)
   int groups = 0;             // window groups pipelined over side streams (0 = automatic, 1 = fully serial launch order)
+  int affine_levels = 0;      // EXPERIMENTAL (default off): leading levels of the bucket sums as batched-affine additions
 };
 
 struct Stats {               // filled per call; read back through ctt_b200_last_stats
@@ -142,6 +144,7 @@ struct Engine {
   cudaEvent_t ev_group[64];
   cudaEvent_t ev_side[2];
   DeviceBuffer d_scalars, d_points, keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_pts[2], part_keys[2], red_a, red_b, bounds;
+  DeviceBuffer work_pts, keys_s, vals_s;   // batched-affine mode: in-place work array, survivor list
   void* h_result = nullptr;   // pinned
   size_t h_result_cap = 0;
   void ensure_host(size_t bytes) {
@@ -278,11 +281,16 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
 
   // level-0 slice length: about twice the mean run length (entries per bucket) so that few slices sit entirely inside
   // one run, but never so long that the grid cannot fill the machine
+  // batched-affine levels (experimental, off by default): the XYZZ accumulation then runs over the survivor list only
+  int AL = E.tuning.affine_levels;
+  if (AL < 0 || entries >= (1ull << 31)) AL = 0;
+  if (AL > 6) AL = 6;
+  const size_t acc_entries = AL ? (entries >> AL) + nbuckets + 1 : entries;   // upper bound of the list k_accumulate walks
   int KACC = 32;
   {
-    double mean_run = (double)entries / (double)nbuckets;
-    while (KACC < 256 && KACC < 2.0 * mean_run && entries / (size_t)(2 * KACC) >= (size_t)4 * 148 * 256) KACC *= 2;
-    if (entries / 32 < (size_t)2 * 148 * 256) KACC = 16;   // fewer than two waves of slices: halve them so the SMs fill evenly
+    double mean_run = (double)acc_entries / (double)nbuckets;
+    while (KACC < 256 && KACC < 2.0 * mean_run && acc_entries / (size_t)(2 * KACC) >= (size_t)4 * 148 * 256) KACC *= 2;
+    if (acc_entries / 32 < (size_t)2 * 148 * 256) KACC = 16;   // fewer than two waves of slices: halve them so the SMs fill evenly
     if (E.tuning.slice_len > 0) KACC = E.tuning.slice_len;
   }
   cudaStream_t s = E.compute();
@@ -338,7 +346,9 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   std::vector<size_t> off0(G + 1, 0), off1(G + 1, 0);
   for (int g = 0; g < G; g++) {
     int w0 = g * Wg, w1 = (w0 + Wg < nw) ? w0 + Wg : nw;
-    size_t max_slices = ((size_t)(w1 - w0) * (table_mode ? (size_t)nwd * n : n) + KACC - 1) / KACC;   // a bucket set holds <= n (table: nwd * n) entries
+    size_t set_cap = table_mode ? (size_t)nwd * n : n;        // a bucket set holds <= n (table: nwd * n) entries
+    if (AL) set_cap = (set_cap >> AL) + B + 1;                // ... of which ceil(run / 2^AL) per bucket survive the affine levels
+    size_t max_slices = ((size_t)(w1 - w0) * set_cap + KACC - 1) / KACC;
     off0[g + 1] = off0[g] + max_slices;
     off1[g + 1] = off1[g] + (max_slices + KFIX - 1) / KFIX;
   }
@@ -363,13 +373,44 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   uint32_t row_final = chunks;
   bool final_in_a = true;
   if (wait_points) B200_CUDA_CHECK(cudaStreamWaitEvent(s, wait_points, 0));
+  const void* acc_points = d_points;
+  if (AL) {
+    constexpr size_t AFF_BYTES = 2 * T::WORDS * 4;
+    uint32_t* starts = dk.Alternate();        // the sort's alternate buffers are free now
+    uint32_t* slots = dv.Alternate();
+    const unsigned long long* total_ptr = (const unsigned long long*)E.bounds.ptr + nw;   // first position of the zero-digit tail
+    E.work_pts.ensure(entries * AFF_BYTES);
+    E.keys_s.ensure(acc_entries * 4);
+    E.vals_s.ensure(acc_entries * 4);
+    size_t tb1 = 0, tb2 = 0;
+    B200_CUDA_CHECK(cub::DeviceScan::InclusiveScan(nullptr, tb1, starts, starts, cub::Max(), (int64_t)entries, s));
+    B200_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tb2, slots, slots, (int64_t)entries, s));
+    E.cub_tmp.ensure(tb1 > tb2 ? tb1 : tb2);
+    const unsigned eb = (unsigned)((entries + 255) / 256);
+    k_run_heads<<<eb, 256, 0, s>>>(keys, entries, starts);
+    B200_CUDA_CHECK(cub::DeviceScan::InclusiveScan(E.cub_tmp.ptr, tb1, starts, starts, cub::Max(), (int64_t)entries, s));
+    for (int r = 0; r < AL; r++) {
+      const size_t threads = (entries + affine_positions_per_thread(r) - 1) / affine_positions_per_thread(r);
+      k_affine_level<T><<<(unsigned)((threads + AFF_THREADS - 1) / AFF_THREADS), AFF_THREADS, 0, s>>>(
+          r, vals, starts, total_ptr, (const uint32_t*)d_points, (uint32_t*)E.work_pts.ptr);
+    }
+    k_survivor_flags<<<eb, 256, 0, s>>>(starts, total_ptr, AL, entries, slots);
+    B200_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(E.cub_tmp.ptr, tb2, slots, slots, (int64_t)entries, s));
+    B200_CUDA_CHECK(cudaMemsetAsync(E.keys_s.ptr, 0xFF, acc_entries * 4, s));   // KEY_NONE: the unused tail sorts last, like zero digits
+    k_survivor_scatter<<<eb, 256, 0, s>>>(keys, starts, slots, total_ptr, AL, entries, (uint32_t*)E.keys_s.ptr, (uint32_t*)E.vals_s.ptr);
+    keys = (const uint32_t*)E.keys_s.ptr;
+    vals = (const uint32_t*)E.vals_s.ptr;
+    acc_points = E.work_pts.ptr;
+    k_window_bounds<<<(unsigned)((nw + 1 + 63) / 64), 64, 0, s>>>(keys, acc_entries, B, nw, (unsigned long long*)E.bounds.ptr);
+    launches += 6 + AL + 4;   // ours + the two scans' kernels
+  }
   for (int g = 0; g < G; g++) {
     const int w0 = g * Wg, w1 = (w0 + Wg < nw) ? w0 + Wg : nw;
     const size_t max_slices = off0[g + 1] - off0[g];
     // 3. accumulate (main stream)
     {
       dim3 block(B200_ACC_THREADS), grid((unsigned)((max_slices + B200_ACC_THREADS - 1) / B200_ACC_THREADS));
-      k_accumulate<T><<<grid, block, 0, s>>>(keys, vals, (const unsigned long long*)E.bounds.ptr, w0, w1, no_key, (const uint32_t*)d_points,
+      k_accumulate<T><<<grid, block, 0, s>>>(keys, vals, (const unsigned long long*)E.bounds.ptr, w0, w1, no_key, (const uint32_t*)acc_points,
                                              (uint32_t*)E.buckets.ptr, (uint32_t*)E.part_pts[0].ptr + off0[g] * XW,
                                              (uint32_t*)E.part_keys[0].ptr + off0[g], max_slices, KACC);
       launches++;

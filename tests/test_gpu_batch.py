@@ -179,3 +179,54 @@ def test_sum_reduce_closed_form_large(M):
     assert lib.ctt_b200_scalar_mul_u64(cv.curve_id, gen, k.ctypes.data, n, pts.ctypes.data) == 0
     e = sum(int(x) for x in k) % cv.fr.modulus
     assert pyref.jac_bytes_to_affine(M.sum_reduce_vartime(cv, pts, n), cv) == pyref.ec_mul_fast(e, cv.gen, cv)
+
+
+# ------------------------------------------------------------------ experimental paths (default off in the library)
+_EXPERIMENTAL = pytest.mark.skipif(__import__("os").environ.get("CTT_B200_TEST_EXPERIMENTAL") != "1",
+                                   reason="experimental batched-affine path: set CTT_B200_TEST_EXPERIMENTAL=1 (not yet validated on a GPU)")
+
+
+@_EXPERIMENTAL
+def test_binary_gcd_inversion_kernel(oracle_lib):
+    """field.cuh fe_inv_gcd through the test hook (op 7: a * inv(a) must be one; zero for a = 0)"""
+    import ctypes
+    from constantine_b200 import _lib
+    from constantine_b200.curves import FIELDS
+    lib = _lib.load()
+    for name, fid in (("bls12_381_fp", 0), ("bn254_snarks_fp", 1), ("pallas_fp", 2), ("vesta_fp", 3)):
+        f = FIELDS[name]
+        r = np.random.default_rng(fid)
+        a = r.integers(0, 256, size=(4096, f.nbytes), dtype=np.uint8)
+        a[:, -1] &= (1 << ((f.bits - 1) % 8)) - 1
+        a[0, :] = 0
+        a[1, :] = 0
+        a[1, 0] = 1
+        out = ctypes.create_string_buffer(a.nbytes)
+        assert lib.ctt_b200_test_field_op(fid, 7, out, a.ctypes.data, a.ctypes.data, len(a)) == 0
+        one = f.one_mont.to_bytes(f.nbytes, "little")
+        got = out.raw
+        assert got[:f.nbytes] == bytes(f.nbytes)
+        assert all(got[i * f.nbytes:(i + 1) * f.nbytes] == one for i in range(1, len(a))), name
+
+
+@_EXPERIMENTAL
+@pytest.mark.parametrize("levels", [1, 2, 3])
+def test_batched_affine_levels_same_results(M, oracle_lib, rng, levels):
+    """ctt_b200_set_affine_levels: the leading levels of the bucket sums as batched-affine additions give the same MSM"""
+    from constantine_b200 import _lib
+    lib = _lib.load()
+    try:
+        lib.ctt_b200_set_affine_levels(levels)
+        for curve, n in (("bls12_381_g1", 5000), ("bn254_snarks_g1", 3001), ("bls12_381_g2", 700), ("pallas_ec", 1)):
+            cv = CURVES[curve]
+            _, pool = point_pool(cv)
+            pts = [pool[rng.randrange(12)] for _ in range(n)]       # few distinct points: P + P and P - P inside the batches
+            if n > 10:
+                pts[3] = None
+            ks = [rng.getrandbits(cv.scalar_bits) for _ in range(n)]
+            cb, pb = pack(cv, ks, pts)
+            want = pyref.jac_bytes_to_affine(oracle_lib.msm(cv, cb, pb, n), cv)
+            got = M.multi_scalar_mul_vartime(cv, cb, pb, n)
+            assert pyref.jac_bytes_to_affine(got, cv) == want, (curve, levels)
+    finally:
+        lib.ctt_b200_set_affine_levels(0)

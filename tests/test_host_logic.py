@@ -111,3 +111,16 @@ def test_batched_affine_schedule_prototype():
     for curve, seed in (("bn254_snarks_g1", 1), ("bls12_381_g2", 2)):
         adds, survivors, n = mod.self_check(curve, n=400, nbuckets=17, seed=seed)
         assert adds > n // 2 and survivors < n // 4
+
+
+def test_binary_gcd_inversion_emulation(rng):
+    """fe_inv_gcd of csrc/field.cuh (the shared inversion of the experimental batched-affine path), emulated on limbs"""
+    import carry_chain_emulation as emu
+    from constantine_b200.curves import FIELDS
+    for name in ("bls12_381_fp", "bn254_snarks_fp", "pallas_fp", "vesta_fp"):
+        f = FIELDS[name]
+        p, n = f.modulus, f.nbytes // 4
+        for a in [1, 2, 3, p - 1, p - 2, (p + 1) // 2] + [rng.randrange(1, p) for _ in range(60)]:
+            got, iters = emu.fe_inv_gcd(p, n, a)
+            assert got == pow(a, -1, p), (name, a)
+            assert iters < 3 * f.bits
