@@ -111,6 +111,9 @@ def test_batched_affine_schedule_prototype():
     for curve, seed in (("bn254_snarks_g1", 1), ("bls12_381_g2", 2)):
         adds, survivors, n = mod.self_check(curve, n=400, nbuckets=17, seed=seed)
         assert adds > n // 2 and survivors < n // 4
+    # thread-accurate simulation of k_affine_level: chunking, per-thread pair capacity, block scan, shared inversion
+    for cap, threads in ((4, 8), (2, 4), (32, 128)):
+        assert mod.self_check_kernel_shape("bn254_snarks_g1", n=500, nbuckets=25, seed=cap, cap=cap, threads=threads) > 0
 
 
 def test_binary_gcd_inversion_emulation(rng):
