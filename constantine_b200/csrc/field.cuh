@@ -476,6 +476,16 @@ __device__ __noinline__ void fe_inv_gcd(uint32_t* r, const uint32_t* a) {
     for (int i = 1; i < N; i++) o |= w[i];
     return o == 0u;
   };
+  {
+    uint32_t nz = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) nz |= u[i];
+    if (nz == 0u) {          // 0 has no inverse: return 0 instead of spinning in the shift loops below
+#pragma unroll
+      for (int i = 0; i < N; i++) r[i] = 0u;
+      return;
+    }
+  }
 #pragma unroll 1
   for (int guard = 0; guard < 4 * 32 * N; guard++) {
     if (is_one(u) || is_one(v)) break;
