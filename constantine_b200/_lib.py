@@ -18,7 +18,8 @@ class Stats(ctypes.Structure):
                 ("ms_h2d", ctypes.c_float), ("ms_digits", ctypes.c_float), ("ms_sort", ctypes.c_float),
                 ("ms_accumulate", ctypes.c_float), ("ms_fixup", ctypes.c_float), ("ms_reduce", ctypes.c_float),
                 ("ms_d2h_tail", ctypes.c_float), ("ms_total", ctypes.c_float),
-                ("groups", ctypes.c_int), ("slice_len", ctypes.c_int)]
+                ("groups", ctypes.c_int), ("slice_len", ctypes.c_int), ("affine_levels", ctypes.c_int),
+                ("ms_affine", ctypes.c_float)]
 
 
 def load():

@@ -440,74 +440,6 @@ B200_DEV void fe_mul_rolled2(uint32_t* r, const uint32_t* a, const uint32_t* b) 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// ---- inversion by the binary extended Euclidean algorithm (plain integers on n limbs) --------------------------------
-// r = a^-1 mod p for 0 < a < p (p odd prime). Data-dependent loops: meant for ONE lane per block (the shared inversion of
-// a batch), where divergence costs nothing and latency is what matters: ~800 shift/subtract steps of ~40 ALU
-// instructions for 381 bits, against the 381 dependent squarings + ~190 multiplications of the Fermat chain.
-// Invariants: x1 * a == u, x2 * a == v (mod p); u, v stay odd-reduced until one of them is 1.
-// (reference: limbs_exgcd.nim runs Pornin's bingcd; this is the textbook form, emulated limb for limb in
-// tests/carry_chain_emulation.py::fe_inv_gcd.)
-template <int N>
-B200_DEV void limbs_shr1(uint32_t* l) {
-#pragma unroll
-  for (int i = 0; i < N - 1; i++) l[i] = __funnelshift_r(l[i], l[i + 1], 1);
-  l[N - 1] >>= 1;
-}
-template <class F>
-B200_DEV void gcd_halve(uint32_t* x) {   // x <- x / 2 mod p   (x + p < 2^(32N): every field has a spare bit)
-  constexpr int N = F::N;
-  if (x[0] & 1u) {
-    x[0] = p_add_cc(x[0], F::P(0));
-#pragma unroll
-    for (int i = 1; i < N - 1; i++) x[i] = p_addc_cc(x[i], F::P(i));
-    x[N - 1] = p_addc(x[N - 1], F::P(N - 1));
-  }
-  limbs_shr1<N>(x);
-}
-template <class F>
-__device__ __noinline__ void fe_inv_gcd(uint32_t* r, const uint32_t* a) {
-  constexpr int N = F::N;
-  uint32_t u[N], v[N], x1[N], x2[N], t[N];
-#pragma unroll
-  for (int i = 0; i < N; i++) { u[i] = a[i]; v[i] = F::P(i); x1[i] = (i == 0) ? 1u : 0u; x2[i] = 0u; }
-  auto is_one = [](const uint32_t* w) {
-    uint32_t o = w[0] ^ 1u;
-#pragma unroll
-    for (int i = 1; i < N; i++) o |= w[i];
-    return o == 0u;
-  };
-  {
-    uint32_t nz = 0;
-#pragma unroll
-    for (int i = 0; i < N; i++) nz |= u[i];
-    if (nz == 0u) {          // 0 has no inverse: return 0 instead of spinning in the shift loops below
-#pragma unroll
-      for (int i = 0; i < N; i++) r[i] = 0u;
-      return;
-    }
-  }
-#pragma unroll 1
-  for (int guard = 0; guard < 4 * 32 * N; guard++) {
-    if (is_one(u) || is_one(v)) break;
-#pragma unroll 1
-    while (!(u[0] & 1u)) { limbs_shr1<N>(u); gcd_halve<F>(x1); }
-#pragma unroll 1
-    while (!(v[0] & 1u)) { limbs_shr1<N>(v); gcd_halve<F>(x2); }
-    const uint32_t borrow = limbs_sub<N>(t, u, v);   // all-ones if u < v
-    if (!borrow) {
-#pragma unroll
-      for (int i = 0; i < N; i++) u[i] = t[i];
-      fe_sub<F>(x1, x1, x2);
-    } else {
-      limbs_sub<N>(v, v, u);
-      fe_sub<F>(x2, x2, x1);
-    }
-  }
-  const bool first = is_one(u);
-#pragma unroll
-  for (int i = 0; i < N; i++) r[i] = first ? x1[i] : x2[i];
-}
-
 // Value types with a common interface (zero/one/is_zero/==, +, -, *, sqr, neg, dbl) so that the
 // elliptic-curve code is written once for G1 (Fp) and G2 (Fp2).
 // ---------------------------------------------------------------------------------------------------------
@@ -600,16 +532,6 @@ struct Fp {
     return r;
   }
   __device__ __noinline__ static void fe_mul_ni(uint32_t* r, const uint32_t* a, const uint32_t* b) { fe_mul<F>(r, a, b); }
-  // Montgomery-form inverse through the binary-GCD routine: this = a R; (a R)^-1 * R^3 * R^-1 = a^-1 R.
-  __device__ __noinline__ Fp inv_gcd() const {
-    Fp t, r2, r3;
-    fe_inv_gcd<F>(t.l, l);
-#pragma unroll
-    for (int i = 0; i < N; i++) r2.l[i] = F::R2(i);
-    fe_mul_ni(r3.l, r2.l, r2.l);   // R^2 * R^2 * R^-1 = R^3
-    fe_mul_ni(t.l, t.l, r3.l);
-    return t;
-  }
 };
 
 // Fp2 = Fp[i] / (i^2 + 1)   (reference extension_fields/towers.nim:39-50: coords[0] + coords[1]*i)
@@ -668,13 +590,6 @@ struct Fp2 {
   B200_DEV void cneg(bool cond) { c0.cneg(cond); c1.cneg(cond); }
   __device__ __noinline__ Fp2 inv() const {
     Base n = (c0.sqr() + c1.sqr()).inv();
-    Fp2 r;
-    r.c0 = c0 * n;
-    r.c1 = (c1 * n).neg();
-    return r;
-  }
-  __device__ __noinline__ Fp2 inv_gcd() const {
-    Base n = (c0.sqr() + c1.sqr()).inv_gcd();
     Fp2 r;
     r.c0 = c0 * n;
     r.c1 = (c1 * n).neg();

@@ -224,7 +224,7 @@ void ctt_b200_set_groups(int groups) {
 void ctt_b200_set_affine_levels(int levels) {
   Engine& E = engine();
   std::lock_guard<std::mutex> lock(E.mu);
-  E.tuning.affine_levels = levels < 0 ? 0 : (levels > 6 ? 6 : levels);
+  E.tuning.affine_levels = levels < 0 ? -1 : (levels > AFF_MAX_LEVELS ? AFF_MAX_LEVELS : levels);   // -1 = automatic
 }
 
 void ctt_b200_set_stream(void* cuda_stream) {

@@ -12,6 +12,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include "msm_kernels.cuh"
+#include "msm_affine.cuh"
 #include "host_field.hpp"
 
 namespace b200 {
@@ -59,7 +60,7 @@ struct Tuning {
   int reduce_chunk = 16;      // L: buckets per bucket-reduce thread
   int slice_len = 0;          // K: sorted entries per accumulate thread (0 = automatic)
   int groups = 0;             // window groups pipelined over side streams (0 = automatic, 1 = fully serial launch order)
-  int affine_levels = 0;      // EXPERIMENTAL (default off): leading levels of the bucket sums as batched-affine additions
+  int affine_levels = -1;     // leading levels of the bucket sums as batched-affine additions: -1 = automatic, 0 = off (XYZZ only)
 };
 
 struct Stats {               // filled per call; read back through ctt_b200_last_stats
@@ -69,6 +70,8 @@ struct Stats {               // filled per call; read back through ctt_b200_last
   int kernel_launches = 0;              // kernels launched by the last call (ours + the radix sort's)
   float ms_h2d = 0, ms_digits = 0, ms_sort = 0, ms_accumulate = 0, ms_fixup = 0, ms_reduce = 0, ms_d2h_tail = 0, ms_total = 0;
   int groups = 1, slice_len = 0;
+  int affine_levels = 0;                // batched-affine levels run by the last call
+  float ms_affine = 0;                  // part of ms_accumulate spent in the plan + batched-affine levels
 };
 
 // Window size: minimise  W*N*MADD + W*2^(c-1)*REDUCE  (same shape as the reference's bestBucketBitSize cost,
@@ -144,7 +147,9 @@ struct Engine {
   cudaEvent_t ev_group[64];
   cudaEvent_t ev_side[2];
   DeviceBuffer d_scalars, d_points, keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_pts[2], part_keys[2], red_a, red_b, bounds;
-  DeviceBuffer work_pts, keys_s, vals_s;   // batched-affine mode: in-place work array, survivor list
+  // batched-affine levels: run bounds, level offsets, per-level plans, two work arrays (odd / even levels), the prefix-product
+  // scratch of the per-thread batch inversions and the survivor list handed to the XYZZ slice kernel
+  DeviceBuffer aff_head, aff_tail, aff_off, aff_blocksum, aff_plan[AFF_MAX_LEVELS], aff_work[2], aff_scratch, keys_s, vals_s;
   void* h_result = nullptr;   // pinned
   size_t h_result_cap = 0;
   void ensure_host(size_t bytes) {
@@ -224,6 +229,17 @@ inline Stats& thread_stats() {
   return s;
 }
 
+// Batched-affine levels pay when a thread's batch is long enough to amortise its inversion (level size / resident threads)
+// and the runs are long enough to have levels at all: large single MSMs. Small / batched calls stay on the XYZZ path.
+inline int auto_affine_levels(size_t entries, size_t nbuckets, size_t batch) {
+  if (batch > 1 || entries < (1ull << 22) || nbuckets == 0) return 0;
+  const double mean_run = (double)entries / (double)nbuckets;
+  int levels = 0;
+  while (levels < 4 && mean_run >= (double)(4u << levels)) levels++;   // mean run 32 -> 4 levels... capped below
+  if (levels > 3) levels = 3;
+  return levels;
+}
+
 // ---- one MSM on device-resident inputs ------------------------------------------------------------------------
 // d_scalars: n x 32 B, d_points: n affine points (ABI layout, Montgomery residues). Produces the window sums in pinned
 // host memory and runs the host tail. Window range [win_begin, win_end) lets several devices split one MSM by windows;
@@ -277,15 +293,18 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   const int nw = (int)nw_total;
   const uint32_t no_key = (uint32_t)nbuckets;
   constexpr size_t XYZZ_BYTES = 4 * T::WORDS * 4;
-  st.c = c; st.num_windows = nwd; st.entries = entries; st.total_buckets = nbuckets;
+  st.c = c; st.num_windows = nwd; st.entries = entries; st.total_buckets = nbuckets; st.ms_affine = 0;
 
   // level-0 slice length: about twice the mean run length (entries per bucket) so that few slices sit entirely inside
   // one run, but never so long that the grid cannot fill the machine
   // batched-affine levels (experimental, off by default): the XYZZ accumulation then runs over the survivor list only
   int AL = E.tuning.affine_levels;
-  if (AL < 0 || entries >= (1ull << 31)) AL = 0;
-  if (AL > 6) AL = 6;
-  const size_t acc_entries = AL ? (entries >> AL) + nbuckets + 1 : entries;   // upper bound of the list k_accumulate walks
+  if (AL < 0) AL = auto_affine_levels(entries, nbuckets, batch);
+  if (entries >= (1ull << 31) || nbuckets >= (1ull << 30)) AL = 0;
+  if (AL > AFF_MAX_LEVELS) AL = AFF_MAX_LEVELS;
+  // level r holds sum_b ceil(n_b / 2^r) <= entries / 2^r + nbuckets slots
+  auto level_cap = [&](int r) { return (entries >> r) + nbuckets + 1; };
+  const size_t acc_entries = AL ? level_cap(AL) : entries;   // upper bound of the list k_accumulate walks
   int KACC = 32;
   {
     double mean_run = (double)acc_entries / (double)nbuckets;
@@ -376,34 +395,63 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   const void* acc_points = d_points;
   if (AL) {
     constexpr size_t AFF_BYTES = 2 * T::WORDS * 4;
-    uint32_t* starts = dk.Alternate();        // the sort's alternate buffers are free now
-    uint32_t* slots = dv.Alternate();
-    const unsigned long long* total_ptr = (const unsigned long long*)E.bounds.ptr + nw;   // first position of the zero-digit tail
-    E.work_pts.ensure(entries * AFF_BYTES);
+    const uint32_t nb = (uint32_t)nbuckets;
+    const uint32_t nblk = (nb + SCAN_ITEMS - 1) / SCAN_ITEMS;
+    const size_t off_stride = (size_t)nb + 1;
+    E.aff_head.ensure((size_t)nb * 4); E.aff_tail.ensure((size_t)nb * 4);
+    E.aff_off.ensure((size_t)(AL + 1) * off_stride * 4);
+    E.aff_blocksum.ensure((size_t)(AL + 1) * nblk * 4);
+    E.aff_plan[0].ensure(level_cap(1) * 8);
+    for (int r = 1; r < AL; r++) E.aff_plan[r].ensure(level_cap(r + 1) * 4);
+    E.aff_work[1].ensure(level_cap(1) * AFF_BYTES);               // odd levels
+    if (AL >= 2) E.aff_work[0].ensure(level_cap(2) * AFF_BYTES);  // even levels
     E.keys_s.ensure(acc_entries * 4);
     E.vals_s.ensure(acc_entries * 4);
-    size_t tb1 = 0, tb2 = 0;
-    B200_CUDA_CHECK(cub::DeviceScan::InclusiveScan(nullptr, tb1, starts, starts, cub::Max(), (int64_t)entries, s));
-    B200_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tb2, slots, slots, (int64_t)entries, s));
-    E.cub_tmp.ensure(tb1 > tb2 ? tb1 : tb2);
-    const unsigned eb = (unsigned)((entries + 255) / 256);
-    k_run_heads<<<eb, 256, 0, s>>>(keys, entries, starts);
-    B200_CUDA_CHECK(cub::DeviceScan::InclusiveScan(E.cub_tmp.ptr, tb1, starts, starts, cub::Max(), (int64_t)entries, s));
-    for (int r = 0; r < AL; r++) {
-      const size_t threads = (entries + affine_positions_per_thread(r) - 1) / affine_positions_per_thread(r);
-      k_affine_level<T><<<(unsigned)((threads + AFF_THREADS - 1) / AFF_THREADS), AFF_THREADS, 0, s>>>(
-          r, vals, starts, total_ptr, (const uint32_t*)d_points, (uint32_t*)E.work_pts.ptr);
-    }
-    k_survivor_flags<<<eb, 256, 0, s>>>(starts, total_ptr, AL, entries, slots);
-    B200_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(E.cub_tmp.ptr, tb2, slots, slots, (int64_t)entries, s));
+    // persistent grid of the pair kernel: as many blocks as stay resident
+    int bps = 0;
+    B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_affine_pairs<T, true>, B200_AFF_THREADS, 0));
+    int bps2 = 0;
+    B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps2, k_affine_pairs<T, false>, B200_AFF_THREADS, 0));
+    if (bps2 < bps) bps = bps2;
+    if (bps < 1) bps = 1;
+    const unsigned aff_grid = (unsigned)(E.sm_count * bps);
+    const size_t aff_threads = (size_t)aff_grid * B200_AFF_THREADS;
+    const size_t per_thread = (level_cap(1) + aff_threads - 1) / aff_threads;
+    E.aff_scratch.ensure(per_thread * aff_threads * (size_t)T::WORDS * 4);
+    uint32_t* head = (uint32_t*)E.aff_head.ptr;
+    uint32_t* tail = (uint32_t*)E.aff_tail.ptr;
+    uint32_t* off = (uint32_t*)E.aff_off.ptr;
+    B200_CUDA_CHECK(cudaMemsetAsync(head, 0, (size_t)nb * 4, s));
+    B200_CUDA_CHECK(cudaMemsetAsync(tail, 0, (size_t)nb * 4, s));
     B200_CUDA_CHECK(cudaMemsetAsync(E.keys_s.ptr, 0xFF, acc_entries * 4, s));   // KEY_NONE: the unused tail sorts last, like zero digits
-    k_survivor_scatter<<<eb, 256, 0, s>>>(keys, starts, slots, total_ptr, AL, entries, (uint32_t*)E.keys_s.ptr, (uint32_t*)E.vals_s.ptr);
+    const unsigned eb = (unsigned)((entries + 255) / 256);
+    k_bucket_bounds<<<eb, 256, 0, s>>>(keys, entries, no_key, head, tail);
+    k_level_blocksums<<<nblk, SCAN_THREADS, 0, s>>>(head, tail, nb, AL, nblk, (uint32_t*)E.aff_blocksum.ptr);
+    k_level_scan<<<1, SCAN_THREADS, 0, s>>>((uint32_t*)E.aff_blocksum.ptr, nblk, AL, nb, off);
+    k_level_offsets<<<nblk, SCAN_THREADS, 0, s>>>(head, tail, nb, AL, nblk, (const uint32_t*)E.aff_blocksum.ptr, off);
+    AffinePlan plan;
+    plan.plan0 = (uint2*)E.aff_plan[0].ptr;
+    for (int r = 0; r < AFF_MAX_LEVELS; r++) plan.plan[r] = (r >= 1 && r < AL) ? (uint32_t*)E.aff_plan[r].ptr : nullptr;
+    plan.surv_keys = (uint32_t*)E.keys_s.ptr;
+    plan.surv_vals = (uint32_t*)E.vals_s.ptr;
+    k_affine_plan<<<eb, 256, 0, s>>>(keys, vals, entries, no_key, head, tail, off, nb, AL, plan);
+    for (int r = 0; r < AL; r++) {
+      const uint32_t* total_ptr = off + (size_t)(r + 1) * off_stride + nb;      // size of level r + 1
+      uint32_t* dst = (uint32_t*)E.aff_work[(r + 1) & 1].ptr;
+      if (r == 0)
+        k_affine_pairs<T, true><<<aff_grid, B200_AFF_THREADS, 0, s>>>(E.aff_plan[0].ptr, total_ptr, (const uint32_t*)d_points, dst, (uint4*)E.aff_scratch.ptr);
+      else
+        k_affine_pairs<T, false><<<aff_grid, B200_AFF_THREADS, 0, s>>>(E.aff_plan[r].ptr, total_ptr, (const uint32_t*)E.aff_work[r & 1].ptr, dst, (uint4*)E.aff_scratch.ptr);
+    }
     keys = (const uint32_t*)E.keys_s.ptr;
     vals = (const uint32_t*)E.vals_s.ptr;
-    acc_points = E.work_pts.ptr;
+    acc_points = E.aff_work[AL & 1].ptr;
     k_window_bounds<<<(unsigned)((nw + 1 + 63) / 64), 64, 0, s>>>(keys, acc_entries, B, nw, (unsigned long long*)E.bounds.ptr);
-    launches += 6 + AL + 4;   // ours + the two scans' kernels
+    launches += 6 + AL;
+    B200_CUDA_CHECK(cudaGetLastError());
+    if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[9], s));
   }
+  st.affine_levels = AL;
   for (int g = 0; g < G; g++) {
     const int w0 = g * Wg, w1 = (w0 + Wg < nw) ? w0 + Wg : nw;
     const size_t max_slices = off0[g + 1] - off0[g];
@@ -497,6 +545,7 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
       cudaEventElapsedTime(&st.ms_digits, E.ev[0], E.ev[1]);
       cudaEventElapsedTime(&st.ms_sort, E.ev[1], E.ev[2]);
       cudaEventElapsedTime(&st.ms_accumulate, E.ev[2], E.ev[3]);
+      if (AL) cudaEventElapsedTime(&st.ms_affine, E.ev[2], E.ev[9]);
       cudaEventElapsedTime(&st.ms_fixup, E.ev[3], E.ev[4]);
       cudaEventElapsedTime(&st.ms_reduce, E.ev[4], E.ev[5]);
       cudaEventElapsedTime(&st.ms_d2h_tail, E.ev[5], E.ev[6]);
@@ -530,6 +579,7 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
     cudaEventElapsedTime(&st.ms_digits, E.ev[0], E.ev[1]);
     cudaEventElapsedTime(&st.ms_sort, E.ev[1], E.ev[2]);
     cudaEventElapsedTime(&st.ms_accumulate, E.ev[2], E.ev[3]);
+    if (AL) cudaEventElapsedTime(&st.ms_affine, E.ev[2], E.ev[9]);
     cudaEventElapsedTime(&st.ms_fixup, E.ev[3], E.ev[4]);
     cudaEventElapsedTime(&st.ms_reduce, E.ev[4], E.ev[5]);
     cudaEventElapsedTime(&st.ms_d2h_tail, E.ev[5], E.ev[6]);

@@ -20,7 +20,7 @@ __global__ void k_test_field_op(int op, uint32_t* r, const uint32_t* a, const ui
     case 3: z = x.neg(); break;
     case 5: z = T::dot2_u(x, y, x + y, x - y); break;   // x y + (x + y)(x - y), one reduction
     case 6: z = x.sqr_u() + y.sqr_u(); break;           // dedicated squaring
-    case 7: z = x.is_zero() ? T::zero() : x.inv_gcd() * x; break;   // binary-GCD inverse: must give one (or zero for x = 0)
+    case 7: z = fe_inverse(x) * x; break;                // safegcd inverse (field_inv.cuh): must give one, or zero for x = 0
     default: z = x.dbl(); break;
   }
   store_words(r + i * T::WORDS, z);

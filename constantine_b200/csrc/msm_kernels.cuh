@@ -393,172 +393,4 @@ __global__ void __launch_bounds__(128) k_sum_strided(const uint32_t* __restrict_
   store_xyzz(out, t, acc);
 }
 
-// ------------------------------------------------------------------------------------------- batched-affine levels
-// EXPERIMENTAL, off by default (ctt_b200_set_affine_levels; schedule prototyped with exact arithmetic in
-// tools/proto_batched_affine.py). The first levels of every bucket sum are done as affine additions that share one
-// inversion per thread block (the reference's choice for c >= 9: sparseVectorAddition / affineAdd,
-// ec_multi_scalar_mul_scheduler.nim:414-553, ec_shortweierstrass_batch_ops.nim:424-455 -- 6 multiplications per addition
-// against 9 for the XYZZ mixed add). A bucket is a run of equal keys in the sorted list; level r pairs the items at run
-// offsets (2i 2^r, (2i+1) 2^r) IN PLACE: the sum replaces the item at the even offset in the work array `work`.
-
-// heads[q] = q if a run starts at q, else 0; an inclusive max-scan turns it into the run start of every position.
-static __global__ void k_run_heads(const uint32_t* __restrict__ keys, size_t total, uint32_t* heads) {
-  size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= total) return;
-  heads[q] = (q == 0 || keys[q] != keys[q - 1]) ? (uint32_t)q : 0u;
-}
-
-template <class T>
-B200_DEV Aff<T> load_affine_rw(const uint32_t* base, size_t idx) {
-  const uint32_t* p = base + idx * (2 * T::WORDS);
-  Aff<T> a;
-  load_words_rw(a.x, p);
-  load_words_rw(a.y, p + T::WORDS);
-  return a;
-}
-template <class T>
-B200_DEV void store_affine(uint32_t* base, size_t idx, const Aff<T>& a) {
-  uint32_t* p = base + idx * (2 * T::WORDS);
-  store_words(p, a.x);
-  store_words(p + T::WORDS, a.y);
-}
-
-// item q of level r: level 0 gathers the input point (sign applied), later levels read the work array
-template <class T>
-B200_DEV Aff<T> affine_item(int r, size_t q, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ points, const uint32_t* work) {
-  if (r == 0) {
-    const uint32_t v = vals[q];
-    Aff<T> p = load_affine<T>(points, v & 0x7FFFFFFFu);
-    if (!p.is_inf()) p.y.cneg((v >> 31) != 0);
-    return p;
-  }
-  return load_affine_rw<T>(work, q);
-}
-
-// lambda = num / den of P1 + P2. Returns 0: result is `triv` (infinity operand or P1 = -P2), no inversion needed;
-// 1: genuine addition or doubling, num / den filled in.
-template <class T>
-B200_DEV int affine_classify(const Aff<T>& P1, const Aff<T>& P2, Aff<T>& triv, T& num, T& den) {
-  if (P1.is_inf()) { triv = P2; return 0; }
-  if (P2.is_inf()) { triv = P1; return 0; }
-  den = P2.x - P1.x;
-  if (den.is_zero()) {
-    num = P2.y - P1.y;
-    if (!num.is_zero() || P1.y.is_zero()) { triv.x = T::zero(); triv.y = T::zero(); return 0; }   // P1 = -P2
-    T xx = P1.x.sqr();
-    num = xx.dbl() + xx;       // doubling: 3 x^2 / 2 y
-    den = P1.y.dbl();
-    return 1;
-  }
-  num = P2.y - P1.y;
-  return 1;
-}
-
-constexpr int AFF_CAP = 32;       // pair slots per thread
-constexpr int AFF_THREADS = 128;
-// positions scanned by one thread at level r: pairs of one thread are at least 2^r + 1 positions apart
-__host__ __device__ inline uint32_t affine_positions_per_thread(int r) { return (uint32_t)(AFF_CAP - 1) * ((1u << r) + 1u); }
-
-template <class T>
-__global__ void __launch_bounds__(AFF_THREADS) k_affine_level(int r, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ starts,
-                                                              const unsigned long long* __restrict__ total_ptr,
-                                                              const uint32_t* __restrict__ points, uint32_t* work) {
-  __shared__ uint32_t sm_pre[AFF_THREADS * T::WORDS], sm_suf[AFF_THREADS * T::WORDS], sm_inv[T::WORDS];
-  const size_t total = (size_t)*total_ptr;
-  const uint32_t step = 1u << r, pc = affine_positions_per_thread(r);
-  const size_t lo = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * pc;
-  const size_t hi = (lo + pc < total) ? lo + pc : total;
-  uint32_t qs[AFF_CAP];
-  T prefix[AFF_CAP];
-  int cnt = 0;
-  T run = T::one();
-  // pass 1: find this thread's pairs, settle the trivial ones, collect the running product of the denominators
-#pragma unroll 1
-  for (size_t q = lo; q < hi; q++) {
-    const uint32_t s = starts[q];
-    if (((uint32_t)q - s) & (2u * step - 1u)) continue;
-    const size_t partner = q + step;
-    if (partner >= total || starts[partner] != s) {
-      if (r == 0) store_affine(work, q, affine_item<T>(0, q, vals, points, work));   // single item: enters the work array
-      continue;
-    }
-    Aff<T> P1 = affine_item<T>(r, q, vals, points, work), P2 = affine_item<T>(r, partner, vals, points, work);
-    Aff<T> triv;
-    T num, den;
-    if (affine_classify(P1, P2, triv, num, den) == 0) { store_affine(work, q, triv); continue; }
-    run = run * den;
-    if (cnt < AFF_CAP) { qs[cnt] = (uint32_t)q; prefix[cnt] = run; }
-    cnt++;
-  }
-  // (cnt <= AFF_CAP by construction: consecutive pair heads are >= 2^r + 1 positions apart)
-  if (!__syncthreads_or(cnt > 0)) return;   // nothing to invert in this block
-  // block-wide inclusive prefix / suffix products of the per-thread products
-  const int tid = threadIdx.x;
-  T pre = run, suf = run;
-  store_words(sm_pre + tid * T::WORDS, pre);
-  store_words(sm_suf + tid * T::WORDS, suf);
-  __syncthreads();
-#pragma unroll 1
-  for (int d = 1; d < AFF_THREADS; d <<= 1) {
-    T a, b;
-    const bool ha = tid >= d, hb = tid + d < AFF_THREADS;
-    if (ha) load_words_rw(a, sm_pre + (tid - d) * T::WORDS);
-    if (hb) load_words_rw(b, sm_suf + (tid + d) * T::WORDS);
-    __syncthreads();
-    if (ha) { pre = pre * a; store_words(sm_pre + tid * T::WORDS, pre); }
-    if (hb) { suf = suf * b; store_words(sm_suf + tid * T::WORDS, suf); }
-    __syncthreads();
-  }
-  if (tid == 0) {
-    T tot;
-    load_words_rw(tot, sm_pre + (AFF_THREADS - 1) * T::WORDS);
-    T inv = tot.inv_gcd();           // THE inversion of this block's batch (one lane; the block waits, other blocks run)
-    store_words(sm_inv, inv);
-  }
-  __syncthreads();
-  if (cnt == 0) return;
-  T inv;
-  load_words_rw(inv, sm_inv);
-  if (tid > 0) { T e; load_words_rw(e, sm_pre + (tid - 1) * T::WORDS); inv = inv * e; }                 // * prod of earlier threads
-  if (tid + 1 < AFF_THREADS) { T e; load_words_rw(e, sm_suf + (tid + 1) * T::WORDS); inv = inv * e; }   // * prod of later threads
-  // inv = 1 / (this thread's product). Pass 2: unwind, newest pair first.
-#pragma unroll 1
-  for (int i = cnt - 1; i >= 0; i--) {
-    const size_t q = qs[i];
-    Aff<T> P1 = affine_item<T>(r, q, vals, points, work), P2 = affine_item<T>(r, q + step, vals, points, work);
-    Aff<T> triv;
-    T num, den;
-    affine_classify(P1, P2, triv, num, den);   // same classification as in pass 1
-    T inv_den = inv;
-    if (i > 0) inv_den = inv * prefix[i - 1];
-    inv = inv * den;
-    T lam = num * inv_den;
-    Aff<T> R;
-    R.x = lam.sqr() - P1.x - P2.x;
-    R.y = lam * (P1.x - R.x) - P1.y;
-    store_affine(work, q, R);
-  }
-}
-
-// Survivors of `levels` levels: the items at run offsets that are multiples of 2^levels. flags -> exclusive sum -> scatter
-// into a short sorted list (key, position in the work array) that the XYZZ accumulation finishes.
-static __global__ void k_survivor_flags(const uint32_t* __restrict__ starts, const unsigned long long* __restrict__ total_ptr, int levels,
-                                        size_t n, uint32_t* flags) {
-  size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n) return;
-  const size_t total = (size_t)*total_ptr;
-  flags[q] = (q < total && ((((uint32_t)q - starts[q]) & ((1u << levels) - 1u)) == 0u)) ? 1u : 0u;
-}
-static __global__ void k_survivor_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ starts, const uint32_t* __restrict__ slot,
-                                          const unsigned long long* __restrict__ total_ptr, int levels, size_t n,
-                                          uint32_t* out_keys, uint32_t* out_vals) {
-  size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n) return;
-  const size_t total = (size_t)*total_ptr;
-  if (q < total && ((((uint32_t)q - starts[q]) & ((1u << levels) - 1u)) == 0u)) {
-    out_keys[slot[q]] = keys[q];
-    out_vals[slot[q]] = (uint32_t)q;     // index into the work array, sign bit clear
-  }
-}
-
 }  // namespace b200

@@ -147,7 +147,9 @@ class CachedBases:
 
     def msm(self, coefs, length=None, out=OUT_JAC, coef_kind="big") -> bytes:
         n = length if length is not None else len(memoryview(coefs).cast("B")) // 32
-        r = ctypes.create_string_buffer(self.curve.jac_bytes)
+        if out not in (OUT_JAC, OUT_PRJ, OUT_XYZZ):
+            raise ValueError("out must be OUT_JAC, OUT_PRJ or OUT_XYZZ")
+        r = ctypes.create_string_buffer(self.curve.coord_bytes * (4 if out == OUT_XYZZ else 3))
         rc = _lib.load().ctt_b200_msm_cached_bases(self._h, out, r, _buf(coefs), n, int(coef_kind == "fr"))
         if rc != 0:
             raise ValueError("ctt_b200_msm_cached_bases failed (len exceeds the cached bases?)")

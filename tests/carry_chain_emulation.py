@@ -200,66 +200,3 @@ def fe_sqr(p, n, a):
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# fe_inv_gcd: binary extended Euclid on n 32-bit limbs (one lane runs it; data-dependent branches are free there).
-def _shr1(l):
-    n = len(l)
-    return [((l[i] >> 1) | ((l[i + 1] & 1) << 31)) & M32 for i in range(n - 1)] + [l[n - 1] >> 1]
-
-
-def _add_limbs(a, b, k):
-    r = [k.add_cc(a[0], b[0])]
-    for i in range(1, len(a) - 1):
-        r.append(k.addc_cc(a[i], b[i]))
-    r.append(k.addc(a[-1], b[-1]))            # asserts: the sum fits n limbs
-    return r
-
-
-def _sub_limbs(a, b):
-    """(a - b mod 2^(32n), borrow)"""
-    r, borrow = [], 0
-    for x, y in zip(a, b):
-        t = x - y - borrow
-        borrow = 1 if t < 0 else 0
-        r.append(t & M32)
-    return r, borrow
-
-
-def fe_inv_gcd(p, n, a):
-    """plain-integer inverse of a mod p as field.cuh fe_inv_gcd computes it; returns (value, loop iterations)."""
-    P = limbs(p, n)
-    k = Flags()
-    u, v = limbs(a, n), list(P)
-    x1, x2 = limbs(1, n), limbs(0, n)
-    one = limbs(1, n)
-    iters = 0
-
-    def halve(x):
-        if x[0] & 1:
-            x = _add_limbs(x, P, k)
-        return _shr1(x)
-
-    def submod(x, y):
-        r, borrow = _sub_limbs(x, y)
-        if borrow:
-            r = [(t) for t in limbs((value(r) + p) & ((1 << (32 * n)) - 1), n)]
-        return r
-
-    while u != one and v != one:
-        while not (u[0] & 1):
-            u = _shr1(u)
-            x1 = halve(x1)
-            iters += 1
-        while not (v[0] & 1):
-            v = _shr1(v)
-            x2 = halve(x2)
-            iters += 1
-        t, borrow = _sub_limbs(u, v)
-        if not borrow:
-            u = t
-            x1 = submod(x1, x2)
-        else:
-            v, _ = _sub_limbs(v, u)
-            x2 = submod(x2, x1)
-        iters += 1
-        assert iters < 4 * 32 * n
-    return value(x1 if u == one else x2), iters

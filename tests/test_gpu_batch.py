@@ -4,6 +4,8 @@ through the C ABI, against the oracle. Shapes follow the reference's own tests:
   tests/parallel/t_ec_template_parallel.nim:84-141                      sum reduction incl. P + P and P - P pairs
   constantine/math/matrix/toeplitz.nim:347-360                          a bank of PrecomputedMSM called one per output
 Bit-exact bar: equality of the affine-normalised results."""
+import random
+
 import numpy as np
 import pytest
 
@@ -182,51 +184,81 @@ def test_sum_reduce_closed_form_large(M):
 
 
 # ------------------------------------------------------------------ experimental paths (default off in the library)
-_EXPERIMENTAL = pytest.mark.skipif(__import__("os").environ.get("CTT_B200_TEST_EXPERIMENTAL") != "1",
-                                   reason="experimental batched-affine path: set CTT_B200_TEST_EXPERIMENTAL=1 (not yet validated on a GPU)")
-
-
-@_EXPERIMENTAL
-def test_binary_gcd_inversion_kernel(oracle_lib):
-    """field.cuh fe_inv_gcd through the test hook (op 7: a * inv(a) must be one; zero for a = 0)"""
+@pytest.mark.gpu
+def test_safegcd_inversion_kernel(oracle_lib):
+    """field_inv.cuh fe_inv_safegcd through the test hook (op 7: a * inv(a) must be one; zero for a = 0), every field"""
     import ctypes
     from constantine_b200 import _lib
     from constantine_b200.curves import FIELDS
     lib = _lib.load()
-    for name, fid in (("bls12_381_fp", 0), ("bn254_snarks_fp", 1), ("pallas_fp", 2), ("vesta_fp", 3)):
+    for fid, name in enumerate(("bls12_381_fp", "bn254_snarks_fp", "pallas_fp", "vesta_fp", "bls12_381_fr", "bn254_snarks_fr",
+                                "pallas_fr", "vesta_fr")):
         f = FIELDS[name]
         r = np.random.default_rng(fid)
-        a = r.integers(0, 256, size=(4096, f.nbytes), dtype=np.uint8)
-        a[:, -1] &= (1 << ((f.bits - 1) % 8)) - 1
+        a = r.integers(0, 256, size=(8192, f.nbytes), dtype=np.uint8)
+        a[:, -1] &= (1 << ((f.bits - 1) % 8)) - 1          # below 2^(bits-1) < p: canonical
         a[0, :] = 0
         a[1, :] = 0
         a[1, 0] = 1
+        a[2, :] = np.frombuffer((f.modulus - 1).to_bytes(f.nbytes, "little"), dtype=np.uint8)
+        a[3, :] = np.frombuffer(f.one_mont.to_bytes(f.nbytes, "little"), dtype=np.uint8)
         out = ctypes.create_string_buffer(a.nbytes)
         assert lib.ctt_b200_test_field_op(fid, 7, out, a.ctypes.data, a.ctypes.data, len(a)) == 0
         one = f.one_mont.to_bytes(f.nbytes, "little")
         got = out.raw
-        assert got[:f.nbytes] == bytes(f.nbytes)
-        assert all(got[i * f.nbytes:(i + 1) * f.nbytes] == one for i in range(1, len(a))), name
+        assert got[:f.nbytes] == bytes(f.nbytes), name
+        bad = [i for i in range(1, len(a)) if got[i * f.nbytes:(i + 1) * f.nbytes] != one]
+        assert not bad, (name, bad[:5])
 
 
-@_EXPERIMENTAL
-@pytest.mark.parametrize("levels", [1, 2, 3])
+@pytest.mark.gpu
+@pytest.mark.parametrize("levels", [1, 2, 3, 5])
 def test_batched_affine_levels_same_results(M, oracle_lib, rng, levels):
-    """ctt_b200_set_affine_levels: the leading levels of the bucket sums as batched-affine additions give the same MSM"""
+    """ctt_b200_set_affine_levels: the leading levels of the bucket sums as batched-affine additions (msm_affine.cuh) give the
+    same MSM as the oracle -- few distinct points, so P + P and P - P land inside the batches; an infinity input; N = 1"""
     from constantine_b200 import _lib
     lib = _lib.load()
     try:
         lib.ctt_b200_set_affine_levels(levels)
-        for curve, n in (("bls12_381_g1", 5000), ("bn254_snarks_g1", 3001), ("bls12_381_g2", 700), ("pallas_ec", 1)):
+        for curve, n in (("bls12_381_g1", 5000), ("bn254_snarks_g1", 3001), ("bls12_381_g2", 700), ("pallas_ec", 1),
+                         ("vesta_ec", 33), ("bn254_snarks_g2", 257)):
             cv = CURVES[curve]
             _, pool = point_pool(cv)
-            pts = [pool[rng.randrange(12)] for _ in range(n)]       # few distinct points: P + P and P - P inside the batches
+            pts = [pool[rng.randrange(12)] for _ in range(n)]
             if n > 10:
                 pts[3] = None
             ks = [rng.getrandbits(cv.scalar_bits) for _ in range(n)]
+            if n > 10:
+                ks[5] = 0
+                ks[6] = ks[7]
+                pts[6] = pts[7]
             cb, pb = pack(cv, ks, pts)
             want = pyref.jac_bytes_to_affine(oracle_lib.msm(cv, cb, pb, n), cv)
             got = M.multi_scalar_mul_vartime(cv, cb, pb, n)
             assert pyref.jac_bytes_to_affine(got, cv) == want, (curve, levels)
+            assert M.last_stats()["affine_levels"] == levels
     finally:
-        lib.ctt_b200_set_affine_levels(0)
+        lib.ctt_b200_set_affine_levels(-1)
+
+
+@pytest.mark.gpu
+def test_batched_affine_adversarial_runs(M):
+    """all scalars equal (one run of N entries per window: log2 N levels would be needed, the XYZZ slices finish it) and all
+    points equal (every level-0 pair is a doubling) -- closed forms"""
+    from constantine_b200 import _lib
+    lib = _lib.load()
+    cv = CURVES["bls12_381_g1"]
+    n = 1 << 14
+    try:
+        lib.ctt_b200_set_affine_levels(3)
+        k = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF1234567890ABCDE
+        g = pyref.aff_to_bytes(cv.gen, cv)
+        got = M.multi_scalar_mul_vartime(cv, pyref.scalar_to_bytes(k, cv) * n, g * n, n)
+        want = pyref.ec_mul_fast(k * n % cv.fr.modulus, cv.gen, cv)
+        assert pyref.jac_bytes_to_affine(got, cv) == want
+        r = random.Random(3)
+        ks = [r.getrandbits(255) for _ in range(n)]
+        got = M.multi_scalar_mul_vartime(cv, b"".join(pyref.scalar_to_bytes(x, cv) for x in ks), g * n, n)
+        assert pyref.jac_bytes_to_affine(got, cv) == pyref.ec_mul_fast(sum(ks) % cv.fr.modulus, cv.gen, cv)
+    finally:
+        lib.ctt_b200_set_affine_levels(-1)

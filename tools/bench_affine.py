@@ -48,7 +48,7 @@ def main():
                 best = st
         print(json.dumps({"curve": a.curve, "logn": a.logn, "affine_levels": lv, "ok": ok,
                           **{kk: round(v, 4) if isinstance(v, float) else v for kk, v in best.items()}}), flush=True)
-    lib.ctt_b200_set_affine_levels(0)
+    lib.ctt_b200_set_affine_levels(-1)
 
 
 if __name__ == "__main__":

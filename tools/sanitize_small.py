@@ -9,6 +9,9 @@ from constantine_b200 import msm as M
 from oracle import oracle
 r = random.Random(3)
 tp = M.Threadpool.new(1)
+if len(sys.argv) > 1:      # forced batched-affine levels (msm_affine.cuh), e.g. `sanitize_small.py 2`
+    from constantine_b200 import _lib
+    _lib.load().ctt_b200_set_affine_levels(int(sys.argv[1]))
 for cv in CURVES.values():
     _, pool = point_pool(cv, size=16)
     for n, same in ((700, False), (900, True)):

@@ -8,7 +8,7 @@
 #include <cuda_runtime.h>
 #include "../constantine_b200/csrc/ec.cuh"
 #include "../constantine_b200/csrc/host_field.hpp"
-#include "../constantine_b200/csrc/field_rr.cuh"
+#include "field_rr.cuh"
 
 using namespace b200;
 
