@@ -71,6 +71,10 @@ def load():
     lib.ctt_b200_set_stream.restype = None
     lib.ctt_b200_sm_count.argtypes = []
     lib.ctt_b200_sm_count.restype = ci
+    lib.ctt_b200_set_devices.argtypes = [ctypes.POINTER(ci), ci]
+    lib.ctt_b200_set_devices.restype = ci
+    lib.ctt_b200_device_count.argtypes = []
+    lib.ctt_b200_device_count.restype = ci
     lib.ctt_b200_test_field_op.argtypes = [ci, ci, vp, vp, vp, sz]
     lib.ctt_b200_test_field_op.restype = ci
     lib.ctt_b200_test_ec_op.argtypes = [ci, ci, vp, vp, vp, sz]

@@ -311,7 +311,7 @@ k_affine_pairs(const void* __restrict__ plan, const uint32_t* __restrict__ total
         const int kind = classify_pair(false, x1, y1, z1 && x1.is_zero(), x2, y2, z2 && x2.is_zero(), den);
         contributes = kind >= PAIR_ADD;
       }
-      if (contributes) run = run * den;
+      if (contributes) run = run.mul_u(den);
       scratch_store(scratch, threads, tid, j, run);
     }
   }
@@ -343,14 +343,15 @@ k_affine_pairs(const void* __restrict__ plan, const uint32_t* __restrict__ total
       else { R.x = T::zero(); R.y = T::zero(); }
     } else {
       T inv_den = inv;
-      if (j > 0) inv_den = inv * scratch_load<T>(scratch, threads, tid, j - 1);
-      inv = inv * den;
+      if (j > 0) inv_den = inv.mul_u(scratch_load<T>(scratch, threads, tid, j - 1));
+      inv = inv.mul_u(den);
       T num;
       if (kind == PAIR_ADD) num = P2.y - P1.y;
-      else { const T xx = P1.x.sqr(); num = xx.dbl() + xx; }     // 3 x^2 (a = 0)
-      const T lam = num * inv_den;
-      R.x = lam.sqr() - P1.x - P2.x;
-      R.y = lam * (P1.x - R.x) - P1.y;
+      else { const T xx = P1.x.sqr(); num = xx.dbl() + xx; }     // 3 x^2 (a = 0); rare: rolled multiplier
+      // unrolled multipliers: the rolled form spends a quarter of its issue slots rotating registers (ncu, profiles/)
+      const T lam = num.mul_u(inv_den);
+      R.x = lam.sqr_u() - P1.x - P2.x;
+      R.y = lam.mul_u(P1.x - R.x) - P1.y;
     }
     store_affine(dst, p, R);
   }

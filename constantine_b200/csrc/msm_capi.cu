@@ -75,8 +75,9 @@ int ctt_b200_plan(int curve_id, size_t len, int force_c, int* c, int* num_window
 #undef X
     default: return -1;
   }
-  Engine& E = engine();
-  int cc = force_c > 0 ? force_c : (E.tuning.force_c > 0 ? E.tuning.force_c : choose_window(len, bits));
+  int tuned_c;
+  { std::lock_guard<std::mutex> lock(config().mu); tuned_c = config().tuning.force_c; }
+  int cc = force_c > 0 ? force_c : (tuned_c > 0 ? tuned_c : choose_window(len, bits));
   if (cc < 2) cc = 2;
   if (cc > 20) cc = 20;
   *c = cc;
@@ -92,9 +93,8 @@ ctt_b200_bases* ctt_b200_bases_upload(int curve_id, const void* points, size_t l
 #undef X
     default: return nullptr;
   }
-  Engine& E = engine();
-  std::lock_guard<std::mutex> lock(E.mu);
-  E.init();
+  EngineLease lease = acquire_engine();
+  Engine& E = *lease.e;
   Bases* b = new Bases;
   b->curve_id = curve_id;
   b->len = len;
@@ -200,44 +200,64 @@ void ctt_b200_last_stats(ctt_b200_stats* out) {
 }
 
 void ctt_b200_set_concurrency(int slots) {
-  Engine& E = engine();
-  std::lock_guard<std::mutex> lock(E.mu);
-  engine_concurrency() = slots < 1 ? 1 : (slots > MAX_ENGINE_SLOTS ? MAX_ENGINE_SLOTS : slots);
+  Config& cfg = config();
+  std::lock_guard<std::mutex> lock(cfg.mu);
+  cfg.concurrency = slots < 1 ? 1 : (slots > MAX_ENGINE_SLOTS ? MAX_ENGINE_SLOTS : slots);
 }
 
 void ctt_b200_set_tuning(int force_c, int reduce_chunk, int slice_len) {
-  Engine& E = engine();
-  std::lock_guard<std::mutex> lock(E.mu);
-  if (force_c > 0) E.tuning.force_c = force_c;
-  if (force_c < 0) E.tuning.force_c = 0;
-  if (reduce_chunk > 0) E.tuning.reduce_chunk = reduce_chunk;
-  if (slice_len > 0) E.tuning.slice_len = slice_len;
-  if (slice_len < 0) E.tuning.slice_len = 0;
+  Config& cfg = config();
+  std::lock_guard<std::mutex> lock(cfg.mu);
+  if (force_c > 0) cfg.tuning.force_c = force_c;
+  if (force_c < 0) cfg.tuning.force_c = 0;
+  if (reduce_chunk > 0) cfg.tuning.reduce_chunk = reduce_chunk;
+  if (slice_len > 0) cfg.tuning.slice_len = slice_len;
+  if (slice_len < 0) cfg.tuning.slice_len = 0;
 }
 
 void ctt_b200_set_groups(int groups) {
-  Engine& E = engine();
-  std::lock_guard<std::mutex> lock(E.mu);
-  E.tuning.groups = groups < 0 ? 0 : groups;
+  Config& cfg = config();
+  std::lock_guard<std::mutex> lock(cfg.mu);
+  cfg.tuning.groups = groups < 0 ? 0 : groups;
 }
 
 void ctt_b200_set_affine_levels(int levels) {
-  Engine& E = engine();
-  std::lock_guard<std::mutex> lock(E.mu);
-  E.tuning.affine_levels = levels < 0 ? -1 : (levels > AFF_MAX_LEVELS ? AFF_MAX_LEVELS : levels);   // -1 = automatic
+  Config& cfg = config();
+  std::lock_guard<std::mutex> lock(cfg.mu);
+  cfg.tuning.affine_levels = levels < 0 ? -1 : (levels > AFF_MAX_LEVELS ? AFF_MAX_LEVELS : levels);   // -1 = automatic
 }
 
 void ctt_b200_set_stream(void* cuda_stream) {
-  Engine& E = engine();
-  std::lock_guard<std::mutex> lock(E.mu);
-  E.user_stream = (cudaStream_t)cuda_stream;
+  primary_device();   // the stream belongs to the caller's current device: bind the engine to it now
+  Config& cfg = config();
+  std::lock_guard<std::mutex> lock(cfg.mu);
+  cfg.user_stream = (cudaStream_t)cuda_stream;
+}
+
+int ctt_b200_set_devices(const int* device_ids, int count) {
+  int present = 0;
+  if (cudaGetDeviceCount(&present) != cudaSuccess) return -1;
+  std::vector<int> v;
+  for (int i = 0; i < count; i++) {
+    if (device_ids[i] < 0 || device_ids[i] >= present) return -1;
+    v.push_back(device_ids[i]);
+  }
+  Config& cfg = config();
+  std::lock_guard<std::mutex> lock(cfg.mu);
+  cfg.devices = v;
+  cfg.devices_from_env_done = true;   // an explicit list overrides CTT_B200_DEVICES
+  return 0;
+}
+
+int ctt_b200_device_count(void) {
+  int present = 0;
+  if (cudaGetDeviceCount(&present) != cudaSuccess) return 0;
+  return present;
 }
 
 int ctt_b200_sm_count(void) {
-  Engine& E = engine();
-  std::lock_guard<std::mutex> lock(E.mu);
-  E.init();
-  return E.sm_count;
+  EngineLease lease = acquire_engine();
+  return lease.e->sm_count;
 }
 
 int ctt_b200_test_field_op(int field_id, int op, void* r, const void* a, const void* b, size_t count) {

@@ -6,7 +6,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <vector>
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
@@ -139,7 +143,9 @@ struct Engine {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
-  cudaStream_t user_stream = nullptr;  // optional caller-provided compute stream (ctt_b200_set_stream)
+  cudaStream_t user_stream = nullptr;  // caller-provided compute stream for this lease (ctt_b200_set_stream), or null
+  cudaStream_t order_after = nullptr;  // caller's stream this lease only orders itself behind (slots other than slot 0)
+  cudaEvent_t ev_order = nullptr;
   cudaStream_t compute() const { return user_stream ? user_stream : stream; }
   cudaStream_t side[2] = {nullptr, nullptr};   // high-priority streams for the fix-up / reduce chains of finished window groups
   cudaEvent_t ev[10];
@@ -162,19 +168,10 @@ struct Engine {
   Stats stats;
   bool collect_timing = true;
 
+  // called with `device` already current on the calling thread (acquire_engine's DeviceGuard)
   void init() {
     if (ready) return;
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0) {
-      fprintf(stderr, "[ctt_b200_msm] FATAL: no CUDA device available (%s). This library has no CPU fallback.\n",
-              cudaGetErrorString(e));
-      abort();
-    }
-    B200_CUDA_CHECK(cudaGetDevice(&device));
-    cudaDeviceProp prop;
-    B200_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-    sm_count = prop.multiProcessorCount;
+    B200_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     B200_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     B200_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     {
@@ -186,42 +183,126 @@ struct Engine {
     }
     for (auto& x : ev) B200_CUDA_CHECK(cudaEventCreate(&x));
     B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_points_ready, cudaEventDisableTiming));
+    B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_order, cudaEventDisableTiming));
     h_result_cap = 1 << 20;
     B200_CUDA_CHECK(cudaMallocHost(&h_result, h_result_cap));
     ready = true;
   }
 };
 
-// Engine slots: slot 0 carries the process-wide settings (tuning, optional user stream) and serves the hooks; concurrent
-// MSM callers (the reference allows nested / concurrent calls, e.g. KZG batch verification issues three MSMs at once,
-// reference constantine/commitments/kzg_parallel.nim:140-172) each lease a free slot with its own streams and scratch
-// buffers, so that the latency-bound tail of one MSM overlaps the accumulate phase of another.
+// ---- process-wide configuration ------------------------------------------------------------------------------
+// Settings live here (guarded by their own mutex), never inside an engine: every lease takes a snapshot while it holds the
+// lock, so a caller that changes the tuning / stream while another thread is inside an MSM cannot race with it.
 constexpr int MAX_ENGINE_SLOTS = 4;
-inline Engine& engine_slot(int i) {
-  static Engine slots[MAX_ENGINE_SLOTS];
-  return slots[i];
+constexpr int MAX_DEVICES = 64;
+struct Config {
+  std::mutex mu;
+  Tuning tuning;
+  cudaStream_t user_stream = nullptr;   // ctt_b200_set_stream
+  int concurrency = 2;                  // engine slots per device handed out to concurrent callers
+  int primary_device = -1;              // the CUDA device current on the thread that made the first call
+  std::vector<int> devices;             // devices a host-pointer MSM is spread over (CTT_B200_DEVICES / ctt_b200_set_devices)
+  bool devices_from_env_done = false;
+  size_t multi_min_len = 1u << 15;      // shorter MSMs stay on the primary device
+};
+inline Config& config() {
+  static Config* c = new Config;        // leaked on purpose: worker threads may outlive static destruction
+  return *c;
 }
-inline Engine& engine() { return engine_slot(0); }
-inline int& engine_concurrency() {
-  static int n = 2;
-  return n;
+
+// RAII: make `dev` the calling thread's current device (the CUDA current device is per host thread; new threads start on
+// device 0), restore the previous one on exit.
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  explicit DeviceGuard(int dev) {
+    B200_CUDA_CHECK(cudaGetDevice(&prev));
+    if (dev >= 0 && prev != dev) { B200_CUDA_CHECK(cudaSetDevice(dev)); changed = true; }
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+  ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+
+// The device every call without an explicit device runs on: whatever was current on the first calling thread (for one
+// process per GPU under torch.distributed: the rank's device), fixed for the life of the process.
+inline int primary_device() {
+  Config& cfg = config();
+  std::lock_guard<std::mutex> lk(cfg.mu);
+  if (cfg.primary_device < 0) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+      fprintf(stderr, "[ctt_b200_msm] FATAL: no CUDA device available (%s). This library has no CPU fallback.\n", cudaGetErrorString(e));
+      abort();
+    }
+    B200_CUDA_CHECK(cudaGetDevice(&cfg.primary_device));
+  }
+  return cfg.primary_device;
+}
+
+// Engine slots, per device: concurrent MSM callers (the reference allows nested / concurrent calls, e.g. KZG batch
+// verification issues three MSMs at once, reference constantine/commitments/kzg_parallel.nim:140-172) each lease a free
+// slot with its own streams and scratch buffers, so that the latency-bound tail of one MSM overlaps the accumulate phase
+// of another.
+struct DeviceCtx {
+  int device = -1;
+  Engine slots[MAX_ENGINE_SLOTS];
+};
+inline DeviceCtx& device_ctx(int device) {
+  static std::mutex mu;
+  static DeviceCtx* table[MAX_DEVICES] = {};
+  if (device < 0 || device >= MAX_DEVICES) { fprintf(stderr, "[ctt_b200_msm] FATAL: bad device ordinal %d\n", device); abort(); }
+  std::lock_guard<std::mutex> lk(mu);
+  if (!table[device]) { table[device] = new DeviceCtx; table[device]->device = device; }
+  return *table[device];
 }
 
 struct EngineLease {
-  Engine* e;
+  std::unique_ptr<DeviceGuard> guard;    // declared first: the device is restored after the slot is released
+  Engine* e = nullptr;
   std::unique_lock<std::mutex> lock;
 };
 
-inline EngineLease acquire_engine() {
-  const int n = engine_concurrency() < 1 ? 1 : (engine_concurrency() > MAX_ENGINE_SLOTS ? MAX_ENGINE_SLOTS : engine_concurrency());
-  for (int i = 0; i < n; i++) {
-    std::unique_lock<std::mutex> lk(engine_slot(i).mu, std::try_to_lock);
-    if (lk.owns_lock()) return EngineLease{&engine_slot(i), std::move(lk)};
+// Lease a slot of `device` (< 0: the primary device), make that device current, initialise the slot on first use and give it
+// a snapshot of the process-wide settings.
+inline EngineLease acquire_engine(int device = -1) {
+  if (device < 0) device = primary_device();
+  Config& cfg = config();
+  EngineLease L;
+  L.guard.reset(new DeviceGuard(device));
+  DeviceCtx& ctx = device_ctx(device);
+  int n;
+  { std::lock_guard<std::mutex> lk(cfg.mu); n = cfg.concurrency; }
+  n = n < 1 ? 1 : (n > MAX_ENGINE_SLOTS ? MAX_ENGINE_SLOTS : n);
+  int slot = -1;
+  for (int i = 0; i < n && slot < 0; i++) {
+    std::unique_lock<std::mutex> lk(ctx.slots[i].mu, std::try_to_lock);
+    if (lk.owns_lock()) { slot = i; L.lock = std::move(lk); }
   }
-  static std::atomic<unsigned> rr{0};
-  int i = (int)(rr.fetch_add(1) % (unsigned)n);
-  std::unique_lock<std::mutex> lk(engine_slot(i).mu);
-  return EngineLease{&engine_slot(i), std::move(lk)};
+  if (slot < 0) {
+    static std::atomic<unsigned> rr{0};
+    slot = (int)(rr.fetch_add(1) % (unsigned)n);
+    L.lock = std::unique_lock<std::mutex>(ctx.slots[slot].mu);
+  }
+  Engine& E = ctx.slots[slot];
+  E.device = device;
+  E.init();
+  {
+    std::lock_guard<std::mutex> lk(cfg.mu);
+    E.tuning = cfg.tuning;
+    // the caller's stream: slot 0 of the primary device launches on it directly; any other slot keeps its own stream but
+    // orders itself behind the work already queued on the caller's stream (device-resident inputs may still be in flight)
+    const bool direct = (slot == 0 && device == cfg.primary_device);
+    E.user_stream = direct ? cfg.user_stream : nullptr;
+    E.order_after = direct ? nullptr : cfg.user_stream;
+  }
+  if (E.order_after && device == primary_device()) {
+    B200_CUDA_CHECK(cudaEventRecord(E.ev_order, E.order_after));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(E.stream, E.ev_order, 0));
+  }
+  L.e = &E;
+  return L;
 }
 
 inline Stats& thread_stats() {
@@ -606,14 +687,12 @@ void write_result(void* r_out, const host::HXyzz<typename C::H>& p, int kind) {
 }
 
 // ---- host-pointer entry (the reference's C ABI semantics): copy in, run, convert ----------------------------------
+// One device: copy `len` pairs in, run the engine, return the raw XYZZ result.
 template <class C>
-void msm_host(void* r_out, const void* coefs, const void* points, size_t len, bool fr_mont, int kind) {
-  EngineLease lease = acquire_engine();
-  Engine& E = *lease.e;
-  E.init();
-  if (&E != &engine()) E.tuning = engine().tuning;
+host::HXyzz<typename C::H> msm_host_on(int device, const void* coefs, const void* points, size_t len, bool fr_mont, Stats* stats_out) {
   using HP = host::HXyzz<typename C::H>;
-  if (len == 0) { write_result<C>(r_out, HP::inf(), kind); return; }  // upstream: UB; here: neutral element
+  EngineLease lease = acquire_engine(device);
+  Engine& E = *lease.e;
   const size_t sbytes = len * 32, pbytes = len * (size_t)(2 * C::COORD_BYTES);
   E.d_scalars.ensure(sbytes);
   E.d_points.ensure(pbytes);
@@ -627,8 +706,143 @@ void msm_host(void* r_out, const void* coefs, const void* points, size_t len, bo
   B200_CUDA_CHECK(cudaEventRecord(t1, E.compute()));
   HP r = msm_device<C>(E, E.d_scalars.ptr, E.d_points.ptr, len, fr_mont, 0, 0, -1, E.ev_points_ready);
   if (E.collect_timing) cudaEventElapsedTime(&E.stats.ms_h2d, t0, t1);
-  thread_stats() = E.stats;
-  write_result<C>(r_out, r, kind);
+  if (stats_out) *stats_out = E.stats;
+  return r;
+}
+
+// Persistent host worker threads, one per entry of the device list: a host-pointer MSM over several GPUs of this process is
+// the reference's "MSM-level parallelism" (ec_multi_scalar_mul_parallel.nim:386-431: the input is cut into chunks, every
+// chunk is a full MSM, the partial results are added) with a GPU per chunk instead of a threadpool task per chunk. Each
+// worker moves only its own N/G pairs over its own PCIe link.
+struct Worker {
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  std::function<void()> job;
+  bool has_job = false, done = true;
+  void loop() {
+    for (;;) {
+      std::function<void()> j;
+      {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return has_job; });
+        j = std::move(job);
+        has_job = false;
+      }
+      j();
+      {
+        std::lock_guard<std::mutex> lk(m);
+        done = true;
+      }
+      cv.notify_all();
+    }
+  }
+  void submit(std::function<void()> j) {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      job = std::move(j);
+      has_job = true;
+      done = false;
+    }
+    cv.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [&] { return done; });
+  }
+};
+struct WorkerPool {
+  std::mutex mu;                        // one multi-device MSM at a time uses the workers
+  std::vector<Worker*> workers;         // leaked with the process (detached threads)
+  void ensure(size_t n) {
+    while (workers.size() < n) {
+      Worker* w = new Worker;
+      w->th = std::thread([w] { w->loop(); });
+      w->th.detach();
+      workers.push_back(w);
+    }
+  }
+};
+inline WorkerPool& worker_pool() {
+  static WorkerPool* p = new WorkerPool;
+  return *p;
+}
+
+// "0,1,2,3", "all", or empty / unset (= the primary device only)
+inline std::vector<int> parse_device_list(const char* txt) {
+  std::vector<int> out;
+  if (!txt || !*txt) return out;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) return out;
+  if (!strcmp(txt, "all")) { for (int i = 0; i < count; i++) out.push_back(i); return out; }
+  const char* p = txt;
+  while (*p) {
+    char* end = nullptr;
+    long v = strtol(p, &end, 10);
+    if (end == p) break;
+    if (v < 0 || v >= count) { fprintf(stderr, "[ctt_b200_msm] FATAL: CTT_B200_DEVICES names device %ld, %d present\n", v, count); abort(); }
+    out.push_back((int)v);
+    p = end;
+    while (*p == ',' || *p == ' ') p++;
+  }
+  return out;
+}
+
+inline std::vector<int> msm_devices() {
+  Config& cfg = config();
+  std::lock_guard<std::mutex> lk(cfg.mu);
+  if (!cfg.devices_from_env_done) {
+    cfg.devices_from_env_done = true;
+    if (cfg.devices.empty()) cfg.devices = parse_device_list(getenv("CTT_B200_DEVICES"));
+    if (const char* m = getenv("CTT_B200_MULTI_MIN_LEN")) cfg.multi_min_len = (size_t)strtoull(m, nullptr, 10);
+  }
+  return cfg.devices;
+}
+
+template <class C>
+void msm_host(void* r_out, const void* coefs, const void* points, size_t len, bool fr_mont, int kind) {
+  using HP = host::HXyzz<typename C::H>;
+  if (len == 0) { write_result<C>(r_out, HP::inf(), kind); return; }  // upstream: UB; here: neutral element
+  const std::vector<int> devs = msm_devices();
+  size_t min_len;
+  { std::lock_guard<std::mutex> lk(config().mu); min_len = config().multi_min_len; }
+  if (devs.size() <= 1 || len < min_len || len < devs.size()) {
+    Stats st;
+    HP r = msm_host_on<C>(devs.size() == 1 ? devs[0] : -1, coefs, points, len, fr_mont, &st);
+    thread_stats() = st;
+    write_result<C>(r_out, r, kind);
+    return;
+  }
+  // several GPUs inside this process: balanced point shards, one worker thread per device, partial results added on the host
+  const size_t G = devs.size();
+  const size_t pt = 2 * (size_t)C::COORD_BYTES;
+  std::vector<HP> parts(G, HP::inf());
+  std::vector<Stats> stats(G);
+  WorkerPool& pool = worker_pool();
+  {
+    std::lock_guard<std::mutex> lk(pool.mu);
+    pool.ensure(G);
+    for (size_t g = 0; g < G; g++) {
+      const size_t lo = len * g / G, hi = len * (g + 1) / G;
+      const int dev = devs[g];
+      HP* dst = &parts[g];
+      Stats* sdst = &stats[g];
+      const char* cp = (const char*)coefs + lo * 32;
+      const char* pp = (const char*)points + lo * pt;
+      pool.workers[g]->submit([=] { *dst = msm_host_on<C>(dev, cp, pp, hi - lo, fr_mont, sdst); });
+    }
+    for (size_t g = 0; g < G; g++) pool.workers[g]->wait();
+  }
+  HP acc = parts[0];
+  for (size_t g = 1; g < G; g++) acc = host::xyzz_add(acc, parts[g]);
+  Stats st = stats[0];
+  for (size_t g = 1; g < G; g++) {   // report the slowest shard's phases, the sum of the work
+    if (stats[g].ms_total > st.ms_total) { const auto e = st.entries + 0; st = stats[g]; st.entries = e; }
+    st.entries += stats[g].entries;
+    st.kernel_launches += stats[g].kernel_launches;
+  }
+  thread_stats() = st;
+  write_result<C>(r_out, acc, kind);
 }
 
 // device-pointer entry (inputs already resident in HBM; used by bench.py `value` and by the cached-bases API)
@@ -637,8 +851,6 @@ void msm_dev_ptrs(void* r_out, const void* d_coefs, const void* d_points, size_t
                   int win_begin, int win_end, size_t table_stride) {
   EngineLease lease = acquire_engine();
   Engine& E = *lease.e;
-  E.init();
-  if (&E != &engine()) E.tuning = engine().tuning;
   using HP = host::HXyzz<typename C::H>;
   E.stats.ms_h2d = 0;
   HP r = msm_device<C>(E, d_coefs, d_points, len, fr_mont, force_c, win_begin, win_end, nullptr, table_stride);
@@ -652,8 +864,6 @@ void msm_cached(void* r_out, const void* coefs, const void* d_points, size_t len
                 size_t table_stride) {
   EngineLease lease = acquire_engine();
   Engine& E = *lease.e;
-  E.init();
-  if (&E != &engine()) E.tuning = engine().tuning;
   using HP = host::HXyzz<typename C::H>;
   E.d_scalars.ensure(len * 32 + 16);
   B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, len * 32, cudaMemcpyHostToDevice, E.compute()));
@@ -680,8 +890,6 @@ void msm_batch_host(void* r_out, const void* coefs, const void* points, size_t b
   if (len == 0) { write_results<C>(r_out, res, kind); return; }
   EngineLease lease = acquire_engine();
   Engine& E = *lease.e;
-  E.init();
-  if (&E != &engine()) E.tuning = engine().tuning;
   const size_t npts = shared_points ? len : batch * len;
   const size_t sbytes = batch * len * 32, pbytes = npts * (size_t)(2 * C::COORD_BYTES);
   E.d_scalars.ensure(sbytes);
@@ -706,8 +914,6 @@ void msm_batch_cached(void* r_out, const void* coefs, const void* d_points, size
   if (len == 0) { write_results<C>(r_out, res, kind); return; }
   EngineLease lease = acquire_engine();
   Engine& E = *lease.e;
-  E.init();
-  if (&E != &engine()) E.tuning = engine().tuning;
   E.d_scalars.ensure(batch * len * 32 + 16);
   B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, batch * len * 32, cudaMemcpyHostToDevice, E.compute()));
   E.stats.ms_h2d = 0;
@@ -726,7 +932,6 @@ void sum_reduce_host(void* r_out, const void* points, size_t len, int kind) {
   if (len >= (1ull << 31)) { fprintf(stderr, "[ctt_b200_msm] FATAL: len >= 2^31 unsupported\n"); abort(); }
   EngineLease lease = acquire_engine();
   Engine& E = *lease.e;
-  E.init();
   cudaStream_t s = E.compute();
   constexpr size_t XYZZ_BYTES = 4 * T::WORDS * 4;
   constexpr size_t XW = 4 * T::WORDS;

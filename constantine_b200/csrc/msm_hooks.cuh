@@ -49,9 +49,8 @@ __global__ void k_test_ec_op(int op, uint32_t* r, const uint32_t* p, const uint3
 
 template <class F>
 int run_test_field_op(int op, void* r, const void* a, const void* b, size_t count) {
-  Engine& E = engine();
-  std::lock_guard<std::mutex> lock(E.mu);
-  E.init();
+  EngineLease lease = acquire_engine();
+  Engine& E = *lease.e;
   size_t bytes = count * F::N64 * 8;
   void *da, *db, *dr;
   B200_CUDA_CHECK(cudaMalloc(&da, bytes + 16)); B200_CUDA_CHECK(cudaMalloc(&db, bytes + 16)); B200_CUDA_CHECK(cudaMalloc(&dr, bytes + 16));
@@ -69,9 +68,8 @@ int run_test_field_op(int op, void* r, const void* a, const void* b, size_t coun
 template <class C>
 int run_test_ec_op(int op, void* r, const void* p, const void* q, size_t count) {
   using T = typename C::T;
-  Engine& E = engine();
-  std::lock_guard<std::mutex> lock(E.mu);
-  E.init();
+  EngineLease lease = acquire_engine();
+  Engine& E = *lease.e;
   size_t in_bytes = count * 2 * C::COORD_BYTES, out_bytes = count * 4 * C::COORD_BYTES;
   void *dp, *dq, *dr;
   B200_CUDA_CHECK(cudaMalloc(&dp, in_bytes + 16)); B200_CUDA_CHECK(cudaMalloc(&dq, in_bytes + 16)); B200_CUDA_CHECK(cudaMalloc(&dr, out_bytes + 16));
@@ -129,9 +127,8 @@ __global__ void __launch_bounds__(128) k_scalar_mul_u64(const uint32_t* base, co
 template <class C>
 int run_scalar_mul_u64(const void* base_aff, const void* k, size_t count, void* out_aff) {
   using T = typename C::T;
-  Engine& E = engine();
-  std::lock_guard<std::mutex> lock(E.mu);
-  E.init();
+  EngineLease lease = acquire_engine();
+  Engine& E = *lease.e;
   size_t pt = 2 * C::COORD_BYTES;
   void *db, *dk, *dout;
   B200_CUDA_CHECK(cudaMalloc(&db, pt + 16)); B200_CUDA_CHECK(cudaMalloc(&dk, count * 8 + 16)); B200_CUDA_CHECK(cudaMalloc(&dout, count * pt + 16));
@@ -186,9 +183,8 @@ __global__ void __launch_bounds__(128) k_precompute_table(const uint32_t* __rest
 template <class C>
 void* run_precompute_table(const void* d_points, size_t n, int c, int* W_out) {
   using T = typename C::T;
-  Engine& E = engine();
-  std::lock_guard<std::mutex> lock(E.mu);
-  E.init();
+  EngineLease lease = acquire_engine();
+  Engine& E = *lease.e;
   const int W = C::SCALAR_BITS / c + 1;
   void* table = nullptr;
   B200_CUDA_CHECK(cudaMalloc(&table, (size_t)W * n * 2 * C::COORD_BYTES + 16));

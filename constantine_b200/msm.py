@@ -54,6 +54,18 @@ class Threadpool:
             self._h = None
 
 
+def set_devices(device_ids) -> None:
+    """Spread every host-pointer MSM of this process over these CUDA devices (ctt_b200_set_devices; [] = caller's device only)."""
+    ids = list(device_ids)
+    arr = (ctypes.c_int * max(1, len(ids)))(*ids)
+    if _lib.load().ctt_b200_set_devices(arr, len(ids)) != 0:
+        raise ValueError(f"unknown CUDA device in {ids}")
+
+
+def device_count() -> int:
+    return _lib.load().ctt_b200_device_count()
+
+
 def _symbol(curve: CurveParams, out: str, coef_kind: str, parallel: bool) -> str:
     return f"ctt_{curve.cprefix}_{out}_multi_scalar_mul_{coef_kind}_coefs_vartime" + ("_parallel" if parallel else "")
 

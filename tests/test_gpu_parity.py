@@ -232,7 +232,7 @@ def test_generator_hook_vs_exact(lib):
 
 
 @pytest.mark.parametrize("curve,logn", [("bn254_snarks_g1", 8), ("bls12_381_g1", 16), ("bls12_381_g1", 20), ("pallas_ec", 20),
-                                        ("bls12_381_g2", 16)])
+                                        ("bls12_381_g2", 16), ("bls12_381_g2", 18)])
 def test_closed_form_at_baseline_sizes(M, lib, tp, curve, logn):
     """points P_i = [k_i]G with known k_i  =>  MSM = [sum s_i k_i mod r] G  (the bug-366 construction generalised,
     SURVEY.md 8c item 4) -- exact at any N, here at BASELINE.json's sizes; plus linearity MSM(s+t) = MSM(s) + MSM(t)."""
@@ -346,3 +346,125 @@ def test_cached_bases_with_precomputed_table(M, oracle_lib, rng):
                 got = pyref.prj_bytes_to_affine(bases.msm(cbm, m, out=M.OUT_PRJ, coef_kind="fr"), cv)
                 assert got == want, (curve, c, m, "fr")
         bases.free()
+
+
+# ------------------------------------------------------------------ skewed scalar distributions of the reference's own tests
+def _scalars_high_hamming_weight(rnd, n, bits):
+    """reference helpers/prng_unsafe.nim:198-216 random_highHammingWeight: every 64-bit limb starts all-ones and loses up to
+    64/3 randomly chosen bits; extra bits over the MSB are cleared."""
+    out = []
+    for _ in range(n):
+        v = 0
+        for limb in range(4):
+            w = (1 << 64) - 1
+            for _ in range(rnd.randrange(64 // 3)):
+                w &= ~(1 << rnd.randrange(64))
+            v |= w << (64 * limb)
+        out.append(v & ((1 << bits) - 1))
+    return out
+
+
+def _scalars_long01(rnd, n, bits):
+    """reference helpers/prng_unsafe.nim:233-260 random_long01Seq: runs of equal bits of length 1 + (u6 * u5 + 16) / 31, read
+    in either byte order."""
+    out = []
+    nbytes = (bits + 7) // 8
+    for _ in range(n):
+        buf = bytearray(nbytes)
+        bit = 0
+        while bit < nbytes * 8:
+            now = 1 + (rnd.randrange(64) * rnd.randrange(32) + 16) // 31
+            val = rnd.randrange(2)
+            while now > 0 and bit < nbytes * 8:
+                buf[bit >> 3] |= val << (bit & 7)
+                now -= 1
+                bit += 1
+        v = int.from_bytes(bytes(buf), rnd.choice(("big", "little")))
+        out.append(v & ((1 << bits) - 1))
+    return out
+
+
+@pytest.mark.parametrize("dist", ["highHammingWeight", "long01Seq"])
+def test_skewed_scalar_distributions_2_18(M, lib, tp, dist):
+    """The reference draws its MSM test scalars from uniform / high-Hamming-weight / long-0-1-run generators
+    (tests/math_elliptic_curves/t_ec_template.nim:1411-1480 with helpers/prng_unsafe.nim:198-260). Same distributions at
+    N = 2^18, BLS12-381 G1 and Pallas, against the closed form; scalars are NOT reduced mod r."""
+    rnd = random.Random(0xC77 + len(dist))
+    for curve in ("bls12_381_g1", "pallas_ec"):
+        cv = CURVES[curve]
+        n = 1 << 18
+        rng = np.random.default_rng(18)
+        k = rng.integers(1, 2**63, size=n, dtype=np.uint64)
+        pts = _gen_points(lib, cv, k)
+        gen = _scalars_high_hamming_weight if dist == "highHammingWeight" else _scalars_long01
+        # 4096 distinct skewed scalars tiled over the N points (generation in Python is the slow part)
+        base = gen(rnd, 4096, cv.scalar_bits)
+        s_int = [base[i & 4095] for i in range(n)]
+        scal = np.frombuffer(b"".join(x.to_bytes(32, "little") for x in base) * (n // 4096), dtype=np.uint8).reshape(n, 32)
+        total = sum(s * int(kk) for s, kk in zip(s_int, k)) % cv.fr.modulus
+        got = M.multi_scalar_mul_vartime_parallel(tp, cv, scal, pts, n)
+        assert pyref.jac_bytes_to_affine(got, cv) == pyref.ec_mul_fast(total, cv.gen, cv), (curve, dist)
+
+
+# ------------------------------------------------------------------ several GPUs / threads inside one process
+def test_in_process_device_list_closed_form(M, lib, tp):
+    """ctt_b200_set_devices: the unchanged C symbol spreads one host-pointer MSM over a device list (point shards, one host
+    worker thread per entry, host addition of the partial points). Every visible GPU is listed; on a one-GPU box the single
+    device is listed twice and then four times, which drives the same code (two engine slots of that device side by side)."""
+    cv = CURVES["bls12_381_g1"]
+    n = (1 << 17) + 5
+    rng = np.random.default_rng(99)
+    k = rng.integers(1, 2**63, size=n, dtype=np.uint64)
+    pts = _gen_points(lib, cv, k)
+    scal = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    scal[:, 31] &= 0x7F
+    s_int = [int.from_bytes(scal[i].tobytes(), "little") for i in range(n)]
+    want = pyref.ec_mul_fast(sum(s * int(kk) for s, kk in zip(s_int, k)) % cv.fr.modulus, cv.gen, cv)
+    count = M.device_count()
+    lists = [list(range(count))] if count > 1 else []
+    lists += [[0, 0], [0, 0, 0, 0]]
+    try:
+        for devs in lists:
+            M.set_devices(devs)
+            got = M.multi_scalar_mul_vartime_parallel(tp, cv, scal, pts, n)
+            assert pyref.jac_bytes_to_affine(got, cv) == want, devs
+            assert M.last_stats()["entries"] > 0
+            # short MSMs stay on one device; N smaller than the list still works
+            g1 = M.multi_scalar_mul_vartime_parallel(tp, cv, scal[:3], pts[:3], 3)
+            w1 = pyref.ec_mul_fast(sum(s * int(kk) for s, kk in zip(s_int[:3], k[:3])) % cv.fr.modulus, cv.gen, cv)
+            assert pyref.jac_bytes_to_affine(g1, cv) == w1
+    finally:
+        M.set_devices([])
+    got = M.multi_scalar_mul_vartime_parallel(tp, cv, scal, pts, n)
+    assert pyref.jac_bytes_to_affine(got, cv) == want
+
+
+def test_caller_thread_with_another_current_device(M, lib, tp, oracle_lib):
+    """The CUDA current device is per host thread and new threads start on device 0: an MSM issued from a worker thread must
+    still run on the device the engine is bound to (every entry point switches to it and restores the caller's device).
+    With two GPUs the worker thread makes the OTHER device current first; with one GPU the thread simply starts fresh."""
+    import threading
+    import torch
+    cv = CURVES["bn254_snarks_g1"]
+    _, pool = point_pool(cv)
+    r = random.Random(5)
+    n = 1500
+    ptsl = [pool[r.randrange(len(pool))] for _ in range(n)]
+    ks = [r.getrandbits(254) for _ in range(n)]
+    cb, pb = pack(cv, ks, ptsl)
+    want = pyref.jac_bytes_to_affine(oracle_lib.msm(cv, cb, pb, n), cv)
+    assert pyref.jac_bytes_to_affine(M.multi_scalar_mul_vartime_parallel(tp, cv, cb, pb, n), cv) == want   # binds the engine
+    bound = torch.cuda.current_device()
+    other = (bound + 1) % max(1, torch.cuda.device_count())
+    out = {}
+
+    def worker():
+        torch.cuda.set_device(other)
+        out["got"] = pyref.jac_bytes_to_affine(M.multi_scalar_mul_vartime_parallel(tp, cv, cb, pb, n), cv)
+        out["dev_after"] = torch.cuda.current_device()
+
+    t = threading.Thread(target=worker)
+    t.start()
+    t.join()
+    assert out["got"] == want
+    assert out["dev_after"] == other          # the caller's current device is restored

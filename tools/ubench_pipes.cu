@@ -24,6 +24,10 @@ enum Mode {
   M_MULWIDE_IADD_CC,    // mul.wide products accumulated with add.cc/addc.cc pairs (carry-deferred column sums)
   M_LOP3,               // xor/and mixes -> LOP3.LUT
   M_SHF,                // funnel shifts -> SHF
+  M_DFMA,               // fma.rn.f64 on 8 chains (all warps)
+  M_WIDE_HALF,          // even warps: chains of 4 mad.lo.cc/madc.hi.cc pairs; odd warps idle
+  M_DFMA_HALF,          // odd warps: fma.rn.f64; even warps idle
+  M_MIX_WIDE_DFMA,      // even warps IMAD.WIDE chains, odd warps DFMA: do the two pipes run side by side?
   M_COUNT
 };
 
@@ -35,6 +39,9 @@ __global__ void k_pipe(uint32_t* out, unsigned long long* cycles, int iters, uin
   uint32_t z0 = 1, z1 = 1, z2 = 1, z3 = 1, z4 = 1, z5 = 1, z6 = 1, z7 = 1;
   uint64_t w0 = 1, w1 = 2, w2 = 3, w3 = 4, w4 = 5, w5 = 6, w6 = 7, w7 = 8;
   w0 += a; w1 += a; w2 += a; w3 += a; w4 += a; w5 += a; w6 += a; w7 += a;   // per-thread values: keep the chains off the uniform datapath
+  double f0 = 1.0 + a, f1 = 2.0 + a, f2 = 3.0, f3 = 4.0, f4 = 5.0, f5 = 6.0, f6 = 7.0, f7 = 8.0;
+  const double fa = 1.0000001 + 1e-9 * threadIdx.x, fb = 1e-7;
+  const bool odd_warp = (threadIdx.x >> 5) & 1;
   __syncthreads();
   const long long t0 = clock64();
 #pragma unroll 1
@@ -95,6 +102,24 @@ __global__ void k_pipe(uint32_t* out, unsigned long long* cycles, int iters, uin
                                     : "+r"(x), "+r"(y), "+r"(z) : "r"(a + k));
       OP(x0, y0, z0, 0) OP(x1, y1, z1, 1) OP(x2, y2, z2, 2) OP(x3, y3, z3, 3) OP(x4, y4, z4, 4) OP(x5, y5, z5, 5) OP(x6, y6, z6, 6) OP(x7, y7, z7, 7)
 #undef OP
+    } else if (MODE == M_DFMA || MODE == M_WIDE_HALF || MODE == M_DFMA_HALF || MODE == M_MIX_WIDE_DFMA) {
+      const bool do_wide = (MODE == M_WIDE_HALF || MODE == M_MIX_WIDE_DFMA) && !odd_warp;
+      const bool do_dfma = MODE == M_DFMA || ((MODE == M_DFMA_HALF || MODE == M_MIX_WIDE_DFMA) && odd_warp);
+      if (do_wide) {
+        asm volatile(
+            "mad.lo.cc.u32 %0, %8, %9, %0; madc.hi.cc.u32 %1, %8, %9, %1; madc.lo.cc.u32 %2, %8, %9, %2; madc.hi.cc.u32 %3, %8, %9, %3;"
+            "madc.lo.cc.u32 %4, %8, %9, %4; madc.hi.cc.u32 %5, %8, %9, %5; madc.lo.cc.u32 %6, %8, %9, %6; madc.hi.u32 %7, %8, %9, %7;"
+            : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7) : "r"(a), "r"(b));
+        asm volatile(
+            "mad.lo.cc.u32 %0, %8, %9, %0; madc.hi.cc.u32 %1, %8, %9, %1; madc.lo.cc.u32 %2, %8, %9, %2; madc.hi.cc.u32 %3, %8, %9, %3;"
+            "madc.lo.cc.u32 %4, %8, %9, %4; madc.hi.cc.u32 %5, %8, %9, %5; madc.lo.cc.u32 %6, %8, %9, %6; madc.hi.u32 %7, %8, %9, %7;"
+            : "+r"(y0), "+r"(y1), "+r"(y2), "+r"(y3), "+r"(y4), "+r"(y5), "+r"(y6), "+r"(y7) : "r"(b), "r"(a));
+      }
+      if (do_dfma) {
+#define OP(x) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(x) : "d"(fa), "d"(fb));
+        OP(f0) OP(f1) OP(f2) OP(f3) OP(f4) OP(f5) OP(f6) OP(f7)
+#undef OP
+      }
     } else if (MODE == M_LOP3) {
 #define OP(x) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x) : "r"(a), "r"(b));
       OP(x0) OP(x1) OP(x2) OP(x3) OP(x4) OP(x5) OP(x6) OP(x7)
@@ -108,7 +133,7 @@ __global__ void k_pipe(uint32_t* out, unsigned long long* cycles, int iters, uin
   const long long t1 = clock64();
   uint32_t r = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7 ^ y0 ^ y1 ^ y2 ^ y3 ^ y4 ^ y5 ^ y6 ^ y7 ^ z0 ^ z1 ^ z2 ^ z3 ^ z4 ^ z5 ^ z6 ^ z7 ^
                (uint32_t)(w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7) ^ (uint32_t)((w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7) >> 32);
-  if (r == 0x12345678u) out[0] = r;
+  if (r == 0x12345678u || f0 + f1 + f2 + f3 + f4 + f5 + f6 + f7 == 0.123) out[0] = r;
   if (threadIdx.x == 0) cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
 }
 
@@ -117,11 +142,12 @@ static const char* kNames[M_COUNT] = {
     "mad.lo.cc+madc.hi single pair (64-bit addend, no carry)", "mad.lo.cc/madc.hi.cc chains of 4 pairs", "chain of 8 pairs",
     "mad.wide.u32 + 64-bit addend as ptxas splits it (IMAD.WIDE RZ + IADD3)", "two dependent add.u32 (IADD3 fusion?) -- op = 2 adds",
     "add.cc chain of 8 (IADD3.X) -- op = 1 add", "mul.wide + 3-word add.cc accumulate -- op = 1 product",
-    "LOP3.LUT", "SHF.R.W"};
+    "LOP3.LUT", "SHF.R.W", "DFMA (fma.rn.f64), all warps", "IMAD.WIDE chains on even warps only (odd idle) -- op = 1 MAC per even-warp thread-op",
+    "DFMA on odd warps only (even idle)", "even warps IMAD.WIDE chains + odd warps DFMA side by side"};
 
 template <int MODE>
-void run(int sms, int blocks_per_sm, int threads) {
-  const int iters = 20000, blocks = sms * blocks_per_sm;
+void run(int sms, int blocks_per_sm, int threads, int iters = 20000) {
+  const int blocks = sms * blocks_per_sm;
   uint32_t* d; unsigned long long* cyc;
   CK(cudaMalloc(&d, 4)); CK(cudaMalloc(&cyc, 8 * blocks));
   k_pipe<MODE><<<blocks, threads>>>(d, cyc, 100, 1);
@@ -136,8 +162,12 @@ void run(int sms, int blocks_per_sm, int threads) {
   CK(cudaMemcpy(h, cyc, 8 * blocks, cudaMemcpyDeviceToHost));
   double mean = 0; for (int i = 0; i < blocks; i++) mean += (double)h[i]; mean /= blocks;
   const double ops_per_sm = (double)blocks_per_sm * threads * iters * 8.0;
-  printf("{\"bench\":\"pipe2\",\"op\":\"%s\",\"warps_per_sm\":%d,\"ms\":%.4f,\"sm_cycles\":%.0f,\"ops_per_clk_per_sm\":%.2f,\"sm_clock_ghz_seen\":%.3f}\n",
-         kNames[MODE], blocks_per_sm * threads / 32, ms, mean, ops_per_sm / mean, mean / (ms * 1e-3) * 1e-9);
+  // ops_per_clk_per_sm / sm_clock_ghz_seen are only meaningful when every block is resident at once (<= 32 registers at 64 warps/SM);
+  // Tops_per_s is time-based and always valid
+  printf("{\"bench\":\"pipe2\",\"op\":\"%s\",\"warps_per_sm\":%d,\"iters\":%d,\"ms\":%.4f,\"Tops_per_s\":%.3f,\"ops_per_clk_per_sm_at_1965MHz\":%.2f,\"sm_cycles\":%.0f,\"ops_per_clk_per_sm\":%.2f,\"sm_clock_ghz_seen\":%.3f}\n",
+         kNames[MODE], blocks_per_sm * threads / 32, iters, ms, ops_per_sm * sms / (ms * 1e-3) * 1e-12, ops_per_sm / (ms * 1e-3 * 1.965e9), mean, ops_per_sm / mean,
+         mean / (ms * 1e-3) * 1e-9);
+  fflush(stdout);
   free(h); cudaFree(d); cudaFree(cyc);
 }
 
@@ -151,5 +181,13 @@ int main() {
   both<M_IMAD_LO>(sms); both<M_IMAD_HI>(sms); both<M_MULWIDE>(sms); both<M_MADWIDE_ADD64>(sms); both<M_MADWIDE_CHAIN4>(sms);
   both<M_MADWIDE_CHAIN12>(sms); both<M_MULWIDE_IADD>(sms); both<M_IADD3>(sms); both<M_IADD_CHAIN8>(sms); both<M_MULWIDE_IADD_CC>(sms);
   both<M_LOP3>(sms); both<M_SHF>(sms);
+  both<M_DFMA>(sms); both<M_WIDE_HALF>(sms); both<M_DFMA_HALF>(sms); both<M_MIX_WIDE_DFMA>(sms);
+  // occupancy sweep of the multiplier-row shape (chains of 4 pairs), long enough (~0.1-0.3 s each) for nvidia-smi to sample clocks and
+  // power beside it (tools/gpu_r2_d.sh): is the sustained rate set by the pipe or by the power cap?
+  run<M_MADWIDE_CHAIN4>(sms, 1, 128, 400000); run<M_MADWIDE_CHAIN4>(sms, 2, 128, 400000); run<M_MADWIDE_CHAIN4>(sms, 4, 128, 400000);
+  run<M_MADWIDE_CHAIN4>(sms, 4, 256, 400000); run<M_MADWIDE_CHAIN4>(sms, 6, 256, 400000);
+  run<M_IMAD_LO>(sms, 2, 128, 800000); run<M_IMAD_LO>(sms, 4, 256, 800000); run<M_IMAD_LO>(sms, 8, 256, 800000);
+  run<M_DFMA>(sms, 2, 128, 400000); run<M_DFMA>(sms, 4, 256, 400000);
+  run<M_MIX_WIDE_DFMA>(sms, 2, 128, 400000); run<M_MIX_WIDE_DFMA>(sms, 4, 256, 400000);
   return 0;
 }
