@@ -49,6 +49,14 @@ INT_MAC_PEAK_PER_S = 9.205e12
 NCU_TRAFFIC_BYTES_N20 = 1.511e9
 
 
+def workload_string(curve, logn):
+    """config.workload, identical in both arms (the driver compares them)."""
+    from constantine_b200.curves import CURVES
+    cv = CURVES[curve]
+    return (f"BLS12-381 G1 MSM N=2^{logn} (BASELINE configs[2]), uniform 255-bit scalars, subgroup points" if curve == "bls12_381_g1"
+            else f"{curve} MSM N=2^{logn}, uniform {cv.scalar_bits}-bit scalars, subgroup points")
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -209,9 +217,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "bls12_381_g1_msm_throughput", "value": v, "unit": "MSM/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"BLS12-381 G1 MSM N=2^{args.logn}, uniform 255-bit scalars", "note":
-                       "CPU restatement (oracle port) of the reference's parallel MSM on all host cores; the Nim reference "
-                       "itself cannot be built in this image"},
+            "config": {"workload": workload_string(CURVE, args.logn), "note":
+                       "portable C restatement (oracle port, NOT Constantine itself: no ADX/MULX assembly, Jacobian buckets) of the "
+                       "reference's parallel MSM on all host cores; the Nim reference cannot be built in this image"},
             "cpu_baseline": {"value": v, "unit": "MSM/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]},
             "e2e": {"value": v, "unit": "MSM/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
@@ -262,11 +270,14 @@ def main():
     # NCCL exchange of <= 8 partial points"). End-to-end leg: the host arrays are sharded by POINTS, so each rank moves only
     # its N/world pairs over PCIe. Both end in one all_gather of <= world partial points + host adds.
     scal_all_seed = 0xC770003
-    scal, pts, _ = make_inputs(n, scal_all_seed)
+    scal, pts, k_dlog = make_inputs(n, scal_all_seed)
     d_scal = torch.from_numpy(scal).to(dev)
     d_pts = torch.from_numpy(pts).to(dev)
     h_scal = torch.from_numpy(np.ascontiguousarray(scal[lo:hi])).pin_memory()
     h_pts = torch.from_numpy(np.ascontiguousarray(pts[lo:hi])).pin_memory()
+    # ordinary (pageable) heap buffers, what a C / Rust / Nim caller of the reference symbol passes
+    pg_scal = np.ascontiguousarray(scal[lo:hi]).copy()
+    pg_pts = np.ascontiguousarray(pts[lo:hi]).copy()
     torch.cuda.synchronize()
     # run the engine on a torch-owned (non-default) stream so that torch.cuda.Event brackets exactly the launches
     bench_stream = torch.cuda.Stream(device=dev)
@@ -292,6 +303,13 @@ def main():
             named(tp._h, r_buf, h_scal.data_ptr(), h_pts.data_ptr(), n_loc)
             return r_buf.raw[:cv.jac_bytes]
         named_xyzz(cv.curve_id, M.OUT_XYZZ, r_buf, h_scal.data_ptr(), h_pts.data_ptr(), n_loc, 0)
+        return sharded.msm_point_sharded(cv, r_buf.raw, device=dev)
+
+    def step_e2e_pageable():
+        if world == 1:
+            named(tp._h, r_buf, pg_scal.ctypes.data, pg_pts.ctypes.data, n_loc)
+            return r_buf.raw[:cv.jac_bytes]
+        named_xyzz(cv.curve_id, M.OUT_XYZZ, r_buf, pg_scal.ctypes.data, pg_pts.ctypes.data, n_loc, 0)
         return sharded.msm_point_sharded(cv, r_buf.raw, device=dev)
 
     def barrier():
@@ -328,14 +346,14 @@ def main():
         sampler.start()
     stats = []
     ms_res, wall_res = timed(step_resident, args.steps, args.warmup, collect=stats.append)
-    ms_e2e, wall_e2e = timed(step_e2e, args.steps, args.warmup)
+    e2e_stats = []
+    ms_e2e, wall_e2e = timed(step_e2e, args.steps, args.warmup, collect=e2e_stats.append)
+    ms_e2e_pg, wall_e2e_pg = timed(step_e2e_pageable, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
-    # per-kernel pass for the roofline: strictly serial launch order (no side-stream overlap) so that the CUDA events
-    # recorded by the engine around k_accumulate bracket that kernel alone
-    lib.ctt_b200_set_groups(1)
-    serial_stats = []
-    ms_serial, _ = timed(step_resident, max(3, args.steps // 2), 2, collect=serial_stats.append)
-    lib.ctt_b200_set_groups(0)
+    # the engine launches strictly in order on one stream, so the CUDA events it records around the accumulation phase bracket
+    # those kernels alone
+    serial_stats = stats
+    ms_serial = ms_res
 
     # Extra (not the headline): two host threads calling concurrently, as the reference's callers may (KZG batch
     # verification issues three MSMs at once). Each thread leases its own engine slot (streams + scratch), so the
@@ -359,10 +377,13 @@ def main():
         concurrent = {"threads": 2, "msms": 2 * per_thread, "value": 2 * per_thread / dt, "unit": "MSM/s",
                       "note": "two concurrent callers, two engine slots; wall clock"}
 
-    # correctness of what was timed: closed form is in tests; here cross-check the two paths against each other
-    ra, rb = step_resident(), step_e2e()
+    # correctness of what was timed: every leg against the closed form  MSM = [sum s_i k_i mod r] G  (the points are k_i G)
+    ra, rb, rc_ = step_resident(), step_e2e(), step_e2e_pageable()
     from oracle import pyref
-    same = pyref.jac_bytes_to_affine(ra, cv) == pyref.jac_bytes_to_affine(rb, cv)
+    s_int = [int.from_bytes(scal[i].tobytes(), "little") for i in range(n)]
+    expect = pyref.ec_mul_fast(sum(a * int(b) for a, b in zip(s_int, k_dlog)) % cv.fr.modulus, cv.gen, cv)
+    legs_ok = [pyref.jac_bytes_to_affine(x, cv) == expect for x in (ra, rb, rc_)]
+    same = all(legs_ok)
 
     if rank != 0:
         if world > 1:
@@ -376,6 +397,14 @@ def main():
     madds = st["entries"]      # bucket point-adds issued by k_accumulate per launch (one per sorted entry, minus run heads)
     macs = madds * INT_MACS_PER_POINT_ADD
     achieved = macs / (acc_ms * 1e-3)
+    # executed MACs: an XYZZ mixed add runs 6 products + 2 squarings + 1 two-product multiplication (2710 MACs for 12 limbs, 8.2 field
+    # multiplications), a batched-affine addition 6 field multiplications; after AL levels ~2^-AL of the entries are left for XYZZ
+    n32 = cv.fp.nbytes // 4
+    fmul = 2 * n32 * n32 + n32
+    al = st["affine_levels"]
+    xyzz_macs = 8.2 * fmul * (3 if cv.ext_degree == 2 else 1)
+    aff_macs = 6.0 * fmul * (3 if cv.ext_degree == 2 else 1)
+    executed = madds * ((1.0 - 2.0 ** -al) * aff_macs + 2.0 ** -al * xyzz_macs) if al else madds * xyzz_macs
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -390,8 +419,7 @@ def main():
         "metric": f"{CURVE}_msm_throughput", "value": 1e3 / ms_res, "unit": "MSM/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": (f"BLS12-381 G1 MSM N=2^{args.logn} (BASELINE configs[2]), uniform 255-bit scalars, subgroup points"
-                                if CURVE == "bls12_381_g1" else f"{CURVE} MSM N=2^{args.logn}, uniform {cv.scalar_bits}-bit scalars, subgroup points"),
+        "config": {"workload": workload_string(CURVE, args.logn),
                    "parallelism": "1 GPU" if world == 1 else (f"resident leg: inputs replicated, {W_plan} windows sharded over {world} GPUs; "
                                                                   f"e2e leg: points sharded over {world} GPUs; both + all_gather of partial points"),
                    "window_c": st["c"], "windows": st["num_windows"],
@@ -400,22 +428,31 @@ def main():
         "wall_ms_per_step": wall_res,
         "e2e": {"value": 1e3 / ms_e2e, "unit": "MSM/s", "ms_per_step": ms_e2e, "wall_ms_per_step": wall_e2e,
                 "h2d_bytes_per_step": int(n_loc * ALGO_BYTES_PER_TERM), "d2h_bytes_per_step": int(st["num_windows"] * 4 * cv.coord_bytes),
-                "api": symbol + " (pinned host buffers)"},
+                "api": symbol + " (pinned host buffers)", "input_chunks_in_flight": "engine default (ctt_b200_set_input_chunks)",
+                "pageable": {"value": 1e3 / ms_e2e_pg, "unit": "MSM/s", "ms_per_step": ms_e2e_pg, "wall_ms_per_step": wall_e2e_pg,
+                             "note": "same call with ordinary malloc'd (pageable) host buffers, as an unmodified caller of the reference symbol passes"}},
         "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
         "phases_ms_serial_launch_order": {k: round(sum(s[k] for s in serial_stats) / len(serial_stats), 4) for k in
                                           ("ms_digits", "ms_sort", "ms_accumulate", "ms_fixup", "ms_reduce", "ms_d2h_tail", "ms_total")},
         "ms_per_step_serial_launch_order": ms_serial, "window_groups": st["groups"], "slice_len": st["slice_len"],
-        "roofline": {"bound": "int32-mad (neither hbm nor tensor: see roofline_hbm)", "kernel": "k_accumulate",
+        "roofline": {"bound": "int32-mad (neither hbm nor tensor: see roofline_hbm)",
+                     "kernel": ("bucket accumulation phase: k_affine_pairs x%d levels + k_accumulate over the survivors" % st["affine_levels"]
+                                if st["affine_levels"] else "k_accumulate"),
                      "achieved": achieved / 1e12, "peak": INT_MAC_PEAK_PER_S / 1e12, "unit": "TMAC/s (32x32->64)",
                      "frac": achieved / INT_MAC_PEAK_PER_S,
+                     "frac_note": "ALGORITHMIC fraction: the unit is the reference's 11-multiplication Jacobian mixed add (3300 MACs, SURVEY.md 8d) per "
+                                  "sorted entry; batched-affine additions execute ~6 multiplications (+ a shared inversion), so the figure may exceed 1",
+                     "frac_executed": executed / (acc_ms * 1e-3) / INT_MAC_PEAK_PER_S, "executed_macs_per_entry": executed / max(1, madds),
                      "traffic": (NCU_TRAFFIC_BYTES_N20 if (world == 1 and args.logn == 20 and st["c"] == 16 and CURVE == "bls12_381_g1") else None),
-                     "traffic_note": "DRAM bytes of one k_accumulate launch from profiles/ncu_k_accumulate_r1.txt; algorithmic gather = entries x 96 B = 1.61e9 B",
-                     "fmaheavy_pipe_busy_ncu": 0.82,
-                     "peak_source": "measured 32x32->64 MAC rate (IMAD.WIDE.U32.X chains, 31.65/clk/SM x 148 SM x 1.965 GHz), tools/ubench.cu -> profiles/ubench_r1.jsonl",
-                     "algorithmic_work": f"{madds} bucket point-adds x {INT_MACS_PER_POINT_ADD} MACs per launch, {acc_ms:.3f} ms"},
+                     "traffic_note": "DRAM bytes (read + write) of the phase's launches from the committed ncu --set full captures (profiles/); "
+                                     "algorithmic gather = entries x 96 B = 1.61e9 B",
+                     "peak_source": "measured 32x32->64 MAC rate of the register-resident Montgomery multiplier loop (IMAD.WIDE.U32.X carry chains, 2 "
+                                    "issue slots each: 31.65 MAC/clk/SM x 148 SM x 1.965 GHz), tools/ubench.cu -> profiles/ubench_r1.jsonl, SASS in profiles/",
+                     "algorithmic_work": f"{madds} bucket point-adds x {INT_MACS_PER_POINT_ADD} MACs per step, {acc_ms:.3f} ms"},
         "roofline_hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                          "traffic": None, "peak_source": hbm_src, "algorithmic_bytes": algo_bytes},
-        "clocks": clocks, "paths_agree": bool(same), "concurrent_callers": concurrent,
+        "clocks": clocks, "paths_agree": bool(same), "closed_form_check": {"resident": legs_ok[0], "e2e_pinned": legs_ok[1], "e2e_pageable": legs_ok[2]},
+        "concurrent_callers": concurrent,
     }
     if not args.no_cpu_baseline and world == 1 and CURVE == "bls12_381_g1":
         line["cpu_baseline"] = {k: v for k, v in time_oracle(n).items() if k in ("value", "unit", "cores", "kind", "sample")}

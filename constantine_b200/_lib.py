@@ -67,6 +67,10 @@ def load():
     lib.ctt_b200_set_groups.restype = None
     lib.ctt_b200_set_affine_levels.argtypes = [ci]
     lib.ctt_b200_set_affine_levels.restype = None
+    lib.ctt_b200_set_reduce_mode.argtypes = [ci]
+    lib.ctt_b200_set_reduce_mode.restype = None
+    lib.ctt_b200_set_input_chunks.argtypes = [ci]
+    lib.ctt_b200_set_input_chunks.restype = None
     lib.ctt_b200_set_stream.argtypes = [vp]
     lib.ctt_b200_set_stream.restype = None
     lib.ctt_b200_sm_count.argtypes = []

@@ -258,8 +258,20 @@ B200_DEV int classify_pair(bool single, const T& x1, const T& y1, bool inf1, con
 #define B200_AFF_THREADS 128
 #endif
 #ifndef B200_AFF_MIN_BLOCKS
-#define B200_AFF_MIN_BLOCKS 3
+#define B200_AFF_MIN_BLOCKS 4      // measured at N = 2^20: 4 blocks (128 registers) 7.50 ms, 3 blocks (141 registers) 7.65 ms per MSM
 #endif
+
+B200_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// both 128-byte lines an operand of `bytes` bytes at p can touch
+B200_DEV void prefetch_span(const void* p, int bytes) {
+  prefetch_l2(p);
+  prefetch_l2((const char*)p + bytes - 1);
+}
+template <class T, bool FIRST>
+B200_DEV void prefetch_point(const uint32_t* src, uint32_t ref) {
+  const uint32_t idx = FIRST ? (ref & 0x7FFFFFFFu) : ref;
+  prefetch_span(src + (size_t)idx * (2 * T::WORDS), 2 * T::WORDS * 4);
+}
 
 // dst[p] = src[a_p] (+ src[b_p]) for p < *total_ptr. Persistent: the grid's threads split the slots evenly; a warp owns a
 // contiguous range of 32 M slots and lane l takes slots l, l + 32, ... of it (coalesced plans, outputs and level >= 1 operands).
@@ -317,12 +329,24 @@ k_affine_pairs(const void* __restrict__ plan, const uint32_t* __restrict__ total
   }
   // ---- the shared inversion of this thread's batch
   T inv = fe_inverse(run);
-  // ---- pass 2: unwind, last slot first
+  // ---- pass 2: unwind, last slot first. The operands of slot j - 1 (found through its plan entry) and the prefix product it
+  // will need are pulled into L2 while slot j is being computed: the dependent plan -> point gather then costs an L2 hit.
+  PairTask t_prev = cnt ? load_task<FIRST>(plan, warp_base + lane + 32u * (size_t)(cnt - 1)) : PairTask{0u, AFF_NONE};
 #pragma unroll 1
   for (uint32_t jj = cnt; jj > 0; jj--) {
     const uint32_t j = jj - 1;
     const size_t p = warp_base + lane + 32u * (size_t)j;
-    const PairTask t = load_task<FIRST>(plan, p);
+    const PairTask t = t_prev;
+    if (j > 0) {
+      t_prev = load_task<FIRST>(plan, p - 32u);
+      prefetch_point<T, FIRST>(src, t_prev.a);
+      if (t_prev.b != AFF_NONE) prefetch_point<T, FIRST>(src, t_prev.b);
+      if (j > 1) {
+        constexpr int V = T::WORDS / 4;
+#pragma unroll
+        for (int k = 0; k < V; k++) prefetch_l2(scratch + ((size_t)(j - 2) * V + k) * threads + tid);
+      }
+    }
     const bool single = t.b == AFF_NONE;
     Aff<T> P1, P2;
     bool z1 = false, z2 = false;

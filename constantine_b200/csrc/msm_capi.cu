@@ -227,6 +227,18 @@ void ctt_b200_set_affine_levels(int levels) {
   cfg.tuning.affine_levels = levels < 0 ? -1 : (levels > AFF_MAX_LEVELS ? AFF_MAX_LEVELS : levels);   // -1 = automatic
 }
 
+void ctt_b200_set_reduce_mode(int mode) {
+  Config& cfg = config();
+  std::lock_guard<std::mutex> lock(cfg.mu);
+  cfg.tuning.reduce_mode = mode == 1 ? 1 : 0;
+}
+
+void ctt_b200_set_input_chunks(int chunks) {
+  Config& cfg = config();
+  std::lock_guard<std::mutex> lock(cfg.mu);
+  cfg.tuning.input_chunks = chunks < 0 ? 0 : chunks;
+}
+
 void ctt_b200_set_stream(void* cuda_stream) {
   primary_device();   // the stream belongs to the caller's current device: bind the engine to it now
   Config& cfg = config();

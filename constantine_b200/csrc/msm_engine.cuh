@@ -63,8 +63,10 @@ struct Tuning {
   int force_c = 0;            // 0 = cost model
   int reduce_chunk = 16;      // L: buckets per bucket-reduce thread
   int slice_len = 0;          // K: sorted entries per accumulate thread (0 = automatic)
-  int groups = 0;             // window groups pipelined over side streams (0 = automatic, 1 = fully serial launch order)
+  int groups = 0;             // retired experiment (window groups over side streams, measured slower): accepted, ignored
   int affine_levels = -1;     // leading levels of the bucket sums as batched-affine additions: -1 = automatic, 0 = off (XYZZ only)
+  int reduce_mode = 0;        // 0 = bit-plane reduction for single MSMs (running-sum chunks for batches), 1 = running-sum chunks always
+  int input_chunks = 0;       // host-pointer MSMs: chunks the input crosses PCIe in (0 = automatic, 1 = one piece)
 };
 
 struct Stats {               // filled per call; read back through ctt_b200_last_stats
@@ -147,12 +149,11 @@ struct Engine {
   cudaStream_t order_after = nullptr;  // caller's stream this lease only orders itself behind (slots other than slot 0)
   cudaEvent_t ev_order = nullptr;
   cudaStream_t compute() const { return user_stream ? user_stream : stream; }
-  cudaStream_t side[2] = {nullptr, nullptr};   // high-priority streams for the fix-up / reduce chains of finished window groups
-  cudaEvent_t ev[10];
+  cudaEvent_t ev[11];
   cudaEvent_t ev_points_ready;
-  cudaEvent_t ev_group[64];
-  cudaEvent_t ev_side[2];
-  DeviceBuffer d_scalars, d_points, keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_pts[2], part_keys[2], red_a, red_b, bounds;
+  static constexpr int MAX_INPUT_CHUNKS = 8;
+  cudaEvent_t ev_chunk[MAX_INPUT_CHUNKS];
+  DeviceBuffer d_scalars, d_points, keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_pts[2], part_keys[2], red_a, red_b, red_planes, bounds;
   // batched-affine levels: run bounds, level offsets, per-level plans, two work arrays (odd / even levels), the prefix-product
   // scratch of the per-thread batch inversions and the survivor list handed to the XYZZ slice kernel
   DeviceBuffer aff_head, aff_tail, aff_off, aff_blocksum, aff_plan[AFF_MAX_LEVELS], aff_work[2], aff_scratch, keys_s, vals_s;
@@ -174,16 +175,10 @@ struct Engine {
     B200_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     B200_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     B200_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-    {
-      int lo = 0, hi = 0;
-      B200_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // hi = numerically lowest = highest priority
-      for (auto& x : side) B200_CUDA_CHECK(cudaStreamCreateWithPriority(&x, cudaStreamNonBlocking, hi));
-      for (auto& x : ev_group) B200_CUDA_CHECK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
-      for (auto& x : ev_side) B200_CUDA_CHECK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
-    }
     for (auto& x : ev) B200_CUDA_CHECK(cudaEventCreate(&x));
     B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_points_ready, cudaEventDisableTiming));
     B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_order, cudaEventDisableTiming));
+    for (auto& x : ev_chunk) B200_CUDA_CHECK(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
     h_result_cap = 1 << 20;
     B200_CUDA_CHECK(cudaMallocHost(&h_result, h_result_cap));
     ready = true;
@@ -206,7 +201,16 @@ struct Config {
   size_t multi_min_len = 1u << 15;      // shorter MSMs stay on the primary device
 };
 inline Config& config() {
-  static Config* c = new Config;        // leaked on purpose: worker threads may outlive static destruction
+  // leaked on purpose: worker threads may outlive static destruction. Environment overrides for experiments are read once:
+  // CTT_B200_INPUT_CHUNKS, CTT_B200_REDUCE_MODE, CTT_B200_AFFINE_LEVELS, CTT_B200_FORCE_C (the set_* calls still win later).
+  static Config* c = [] {
+    Config* x = new Config;
+    if (const char* v = getenv("CTT_B200_INPUT_CHUNKS")) x->tuning.input_chunks = atoi(v);
+    if (const char* v = getenv("CTT_B200_REDUCE_MODE")) x->tuning.reduce_mode = atoi(v) == 1 ? 1 : 0;
+    if (const char* v = getenv("CTT_B200_AFFINE_LEVELS")) x->tuning.affine_levels = atoi(v);
+    if (const char* v = getenv("CTT_B200_FORCE_C")) x->tuning.force_c = atoi(v);
+    return x;
+  }();
   return *c;
 }
 
@@ -333,11 +337,21 @@ inline int auto_affine_levels(size_t entries, size_t nbuckets, size_t batch) {
 // ec_multi_scalar_mul_precomp.nim:192-240 called per output in matrix/toeplitz.nim:347-360) fill the machine like one
 // large MSM does. d_scalars = batch*n scalars; d_points = batch*n points, or n points when `shared_points`; the
 // results are written to batch_out[0..batch) and the tail (Horner per MSM) runs on the device.
+// Input chunks (single MSMs from host memory): the pairs arrive in consecutive chunks, each guarded by an event of the copy
+// stream. Digits, sort and bucket accumulation run per chunk INTO THE SAME buckets (a run that opens a bucket starts from
+// the bucket's current value), so the engine works on chunk k while chunk k+1 is still crossing PCIe; the bucket reduction
+// and the tail run once.
+struct InputChunk {
+  size_t begin, count;          // pairs [begin, begin + count)
+  cudaEvent_t ready;            // recorded on the copy stream after the chunk's scalars and points (may be null)
+};
+
 template <class C>
 host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const void* d_points, size_t n, bool fr_mont,
                                       int force_c, int win_begin, int win_end, cudaEvent_t wait_points = nullptr,
                                       size_t table_stride = 0, size_t batch = 1, bool shared_points = false,
-                                      host::HXyzz<typename C::H>* batch_out = nullptr) {
+                                      host::HXyzz<typename C::H>* batch_out = nullptr,
+                                      const std::vector<InputChunk>* input_chunks = nullptr) {
   using T = typename C::T;
   using H = typename C::H;
   using HP = host::HXyzz<H>;
@@ -349,11 +363,12 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
     if (batch_out) for (size_t m = 0; m < batch; m++) batch_out[m] = HP::inf();
     return HP::inf();
   }
-  const size_t ntot = batch * n;                           // scalars in this call
-  if (ntot >= (1ull << 31)) { fprintf(stderr, "[ctt_b200_msm] FATAL: len >= 2^31 unsupported\n"); abort(); }
+  if (batch * n >= (1ull << 31)) { fprintf(stderr, "[ctt_b200_msm] FATAL: len >= 2^31 unsupported\n"); abort(); }
   if (batch > 1 && (batch_out == nullptr || win_begin != 0 || win_end >= 0)) {
     fprintf(stderr, "[ctt_b200_msm] FATAL: a batch takes all windows and needs an output array\n"); abort();
   }
+  const bool table_mode = table_stride > 0;
+  if (input_chunks && (batch > 1 || table_mode || input_chunks->empty())) input_chunks = nullptr;
 
   int c = force_c > 0 ? force_c : (E.tuning.force_c > 0 ? E.tuning.force_c : choose_window(n, C::SCALAR_BITS));
   if (c < 2) c = 2;
@@ -361,311 +376,332 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   DigitPlan plan = make_plan(C::SCALAR_BITS, c, win_begin, win_end);
   const int nwd = plan.win_end - plan.win_begin;          // digit windows handled by this call
   if (nwd <= 0) return HP::inf();
-  const bool table_mode = table_stride > 0;
   const int nws = table_mode ? 1 : nwd;                   // bucket sets per MSM
   const size_t nw_total = batch * (size_t)nws;            // bucket sets ("logical windows") of the call
-  const size_t entries = (size_t)nwd * ntot;
   if (table_mode && (size_t)nwd * table_stride >= (1ull << 31)) { fprintf(stderr, "[ctt_b200_msm] FATAL: table too large\n"); abort(); }
   const uint32_t B = plan.buckets_per_window;
   const size_t nbuckets = nw_total * B;
-  if (nbuckets >= 0xFFFFFFF0ull || nw_total >= (1ull << 30) || entries >= (1ull << 32)) {
+  if (nbuckets >= 0xFFFFFFF0ull || nw_total >= (1ull << 30) || (size_t)nwd * batch * n >= (1ull << 32)) {
     fprintf(stderr, "[ctt_b200_msm] FATAL: batch too large for 32-bit bucket keys\n"); abort();
   }
   const int nw = (int)nw_total;
   const uint32_t no_key = (uint32_t)nbuckets;
   constexpr size_t XYZZ_BYTES = 4 * T::WORDS * 4;
-  st.c = c; st.num_windows = nwd; st.entries = entries; st.total_buckets = nbuckets; st.ms_affine = 0;
-
-  // level-0 slice length: about twice the mean run length (entries per bucket) so that few slices sit entirely inside
-  // one run, but never so long that the grid cannot fill the machine
-  // batched-affine levels (experimental, off by default): the XYZZ accumulation then runs over the survivor list only
-  int AL = E.tuning.affine_levels;
-  if (AL < 0) AL = auto_affine_levels(entries, nbuckets, batch);
-  if (entries >= (1ull << 31) || nbuckets >= (1ull << 30)) AL = 0;
-  if (AL > AFF_MAX_LEVELS) AL = AFF_MAX_LEVELS;
-  // level r holds sum_b ceil(n_b / 2^r) <= entries / 2^r + nbuckets slots
-  auto level_cap = [&](int r) { return (entries >> r) + nbuckets + 1; };
-  const size_t acc_entries = AL ? level_cap(AL) : entries;   // upper bound of the list k_accumulate walks
-  int KACC = 32;
-  {
-    double mean_run = (double)acc_entries / (double)nbuckets;
-    while (KACC < 256 && KACC < 2.0 * mean_run && acc_entries / (size_t)(2 * KACC) >= (size_t)4 * 148 * 256) KACC *= 2;
-    if (acc_entries / 32 < (size_t)2 * 148 * 256) KACC = 16;   // fewer than two waves of slices: halve them so the SMs fill evenly
-    if (E.tuning.slice_len > 0) KACC = E.tuning.slice_len;
-  }
-  cudaStream_t s = E.compute();
-  E.keys_a.ensure(entries * 4); E.keys_b.ensure(entries * 4);
-  E.vals_a.ensure(entries * 4); E.vals_b.ensure(entries * 4);
-  E.buckets.ensure(nbuckets * XYZZ_BYTES);
-
-  if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[0], s));
-  // 1. digits
-  {
-    dim3 grid((unsigned)((ntot + 255) / 256)), block(256);
-    const uint32_t msm_key_stride = (uint32_t)nws * B, shared = shared_points ? 1u : 0u;
-    if (fr_mont)
-      k_digits<typename C::FrParams, true><<<grid, block, 0, s>>>((const uint32_t*)d_scalars, (uint32_t)ntot, plan, (uint32_t*)E.keys_a.ptr, (uint32_t*)E.vals_a.ptr,
-                                                                   table_mode ? 0u : B, no_key, (uint32_t)table_stride, (uint32_t)n, msm_key_stride, shared);
-    else
-      k_digits<typename C::FrParams, false><<<grid, block, 0, s>>>((const uint32_t*)d_scalars, (uint32_t)ntot, plan, (uint32_t*)E.keys_a.ptr, (uint32_t*)E.vals_a.ptr,
-                                                                    table_mode ? 0u : B, no_key, (uint32_t)table_stride, (uint32_t)n, msm_key_stride, shared);
-    launches++;
-  }
-  if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[1], s));
-  // 2. sort by key
-  int end_bit = 1;
-  while ((1ull << end_bit) <= (unsigned long long)no_key) end_bit++;
-  cub::DoubleBuffer<uint32_t> dk((uint32_t*)E.keys_a.ptr, (uint32_t*)E.keys_b.ptr);
-  cub::DoubleBuffer<uint32_t> dv((uint32_t*)E.vals_a.ptr, (uint32_t*)E.vals_b.ptr);
-  {
-    size_t tmp_bytes = 0;
-    B200_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int64_t)entries, 0, end_bit, s));
-    E.cub_tmp.ensure(tmp_bytes);
-    B200_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(E.cub_tmp.ptr, tmp_bytes, dk, dv, (int64_t)entries, 0, end_bit, s));
-    launches += 2 + (end_bit + 7) / 8;  // histogram + exclusive-sum + one onesweep pass per 8 key bits
-  }
-  const uint32_t* keys = dk.Current();
-  const uint32_t* vals = dv.Current();
-  B200_CUDA_CHECK(cudaMemsetAsync(E.buckets.ptr, 0, nbuckets * XYZZ_BYTES, s));  // all-zero XYZZ = infinity
-  if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[2], s));
-  // window groups: the sorted list is ordered by window, so the windows are cut into G consecutive groups whose
-  // accumulate launches run back to back on the main stream while the latency-bound fix-up / reduce chain of every
-  // finished group runs on a high-priority side stream underneath the next group's accumulate.
-  // Measured on B200 at N = 2^20 (profiles/README.md): splitting the accumulate into per-group launches costs more in
-  // partial waves than the overlap wins back, so the default is ONE group; the knob stays for experiments.
-  int G = E.tuning.groups > 0 ? E.tuning.groups : 1;
-  if (G > nw) G = nw;
-  if (G > 32) G = 32;
-  const int Wg = (nw + G - 1) / G;
-  G = (nw + Wg - 1) / Wg;
-  st.groups = G; st.slice_len = KACC;
-  E.bounds.ensure((size_t)(nw + 1) * 8);
-  k_window_bounds<<<(unsigned)((nw + 1 + 63) / 64), 64, 0, s>>>(keys, entries, B, nw, (unsigned long long*)E.bounds.ptr);
-  launches++;
-  // per-group geometry (upper bounds known on the host; the exact entry ranges stay on the device)
-  std::vector<size_t> off0(G + 1, 0), off1(G + 1, 0);
-  for (int g = 0; g < G; g++) {
-    int w0 = g * Wg, w1 = (w0 + Wg < nw) ? w0 + Wg : nw;
-    size_t set_cap = table_mode ? (size_t)nwd * n : n;        // a bucket set holds <= n (table: nwd * n) entries
-    if (AL) set_cap = (set_cap >> AL) + B + 1;                // ... of which ceil(run / 2^AL) per bucket survive the affine levels
-    size_t max_slices = ((size_t)(w1 - w0) * set_cap + KACC - 1) / KACC;
-    off0[g + 1] = off0[g] + max_slices;
-    off1[g + 1] = off1[g] + (max_slices + KFIX - 1) / KFIX;
-  }
-  E.part_pts[0].ensure(off0[G] * XYZZ_BYTES); E.part_keys[0].ensure(off0[G] * 4);
-  E.part_pts[1].ensure(off1[G] * XYZZ_BYTES); E.part_keys[1].ensure(off1[G] * 4);
+  constexpr size_t XW = 4 * T::WORDS;  // 32-bit words per XYZZ point
+  constexpr size_t AFF_BYTES = 2 * T::WORDS * 4;
+  st.c = c; st.num_windows = nwd; st.total_buckets = nbuckets; st.ms_affine = 0; st.entries = 0; st.groups = 1;
 #ifndef B200_INLINE_MAX_WORDS
 #define B200_INLINE_MAX_WORDS 12
 #endif
   constexpr bool INL = (T::WORDS <= B200_INLINE_MAX_WORDS);   // single-field coordinates: inline the point adds; Fp2: out-of-line (code size)
-  uint32_t L = (uint32_t)E.tuning.reduce_chunk;
-  if (L < 1) L = 1;
-  uint32_t chunks = (B + L - 1) / L;
-  // small bucket counts: the phase is a chain of dependent point operations, so trade chunk length for more threads
-  // (a larger target for Fp2 was measured slower: the offset multiplication per chunk dominates then)
-  const size_t want_threads = (size_t)E.sm_count * 64;
-  while (L > 1 && (size_t)chunks * nw < want_threads && chunks < B) { L = (L + 1) / 2; chunks = (B + L - 1) / L; }
-  int nbits = 0;
-  while (nbits < 32 && ((uint64_t)(chunks - 1) * L >> nbits) != 0) nbits++;
-  E.red_a.ensure((size_t)chunks * nw * XYZZ_BYTES);
-  E.red_b.ensure((size_t)chunks * nw * XYZZ_BYTES);
-  constexpr size_t XW = 4 * T::WORDS;  // 32-bit words per XYZZ point
-  uint32_t row_final = chunks;
-  bool final_in_a = true;
-  if (wait_points) B200_CUDA_CHECK(cudaStreamWaitEvent(s, wait_points, 0));
-  const void* acc_points = d_points;
-  if (AL) {
-    constexpr size_t AFF_BYTES = 2 * T::WORDS * 4;
-    const uint32_t nb = (uint32_t)nbuckets;
-    const uint32_t nblk = (nb + SCAN_ITEMS - 1) / SCAN_ITEMS;
-    const size_t off_stride = (size_t)nb + 1;
-    E.aff_head.ensure((size_t)nb * 4); E.aff_tail.ensure((size_t)nb * 4);
-    E.aff_off.ensure((size_t)(AL + 1) * off_stride * 4);
-    E.aff_blocksum.ensure((size_t)(AL + 1) * nblk * 4);
-    E.aff_plan[0].ensure(level_cap(1) * 8);
-    for (int r = 1; r < AL; r++) E.aff_plan[r].ensure(level_cap(r + 1) * 4);
-    E.aff_work[1].ensure(level_cap(1) * AFF_BYTES);               // odd levels
-    if (AL >= 2) E.aff_work[0].ensure(level_cap(2) * AFF_BYTES);  // even levels
-    E.keys_s.ensure(acc_entries * 4);
-    E.vals_s.ensure(acc_entries * 4);
-    // persistent grid of the pair kernel: as many blocks as stay resident
-    int bps = 0;
-    B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_affine_pairs<T, true>, B200_AFF_THREADS, 0));
-    int bps2 = 0;
-    B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps2, k_affine_pairs<T, false>, B200_AFF_THREADS, 0));
-    if (bps2 < bps) bps = bps2;
-    if (bps < 1) bps = 1;
-    const unsigned aff_grid = (unsigned)(E.sm_count * bps);
-    const size_t aff_threads = (size_t)aff_grid * B200_AFF_THREADS;
-    const size_t per_thread = (level_cap(1) + aff_threads - 1) / aff_threads;
-    E.aff_scratch.ensure(per_thread * aff_threads * (size_t)T::WORDS * 4);
-    uint32_t* head = (uint32_t*)E.aff_head.ptr;
-    uint32_t* tail = (uint32_t*)E.aff_tail.ptr;
-    uint32_t* off = (uint32_t*)E.aff_off.ptr;
-    B200_CUDA_CHECK(cudaMemsetAsync(head, 0, (size_t)nb * 4, s));
-    B200_CUDA_CHECK(cudaMemsetAsync(tail, 0, (size_t)nb * 4, s));
-    B200_CUDA_CHECK(cudaMemsetAsync(E.keys_s.ptr, 0xFF, acc_entries * 4, s));   // KEY_NONE: the unused tail sorts last, like zero digits
-    const unsigned eb = (unsigned)((entries + 255) / 256);
-    k_bucket_bounds<<<eb, 256, 0, s>>>(keys, entries, no_key, head, tail);
-    k_level_blocksums<<<nblk, SCAN_THREADS, 0, s>>>(head, tail, nb, AL, nblk, (uint32_t*)E.aff_blocksum.ptr);
-    k_level_scan<<<1, SCAN_THREADS, 0, s>>>((uint32_t*)E.aff_blocksum.ptr, nblk, AL, nb, off);
-    k_level_offsets<<<nblk, SCAN_THREADS, 0, s>>>(head, tail, nb, AL, nblk, (const uint32_t*)E.aff_blocksum.ptr, off);
-    AffinePlan plan;
-    plan.plan0 = (uint2*)E.aff_plan[0].ptr;
-    for (int r = 0; r < AFF_MAX_LEVELS; r++) plan.plan[r] = (r >= 1 && r < AL) ? (uint32_t*)E.aff_plan[r].ptr : nullptr;
-    plan.surv_keys = (uint32_t*)E.keys_s.ptr;
-    plan.surv_vals = (uint32_t*)E.vals_s.ptr;
-    k_affine_plan<<<eb, 256, 0, s>>>(keys, vals, entries, no_key, head, tail, off, nb, AL, plan);
-    for (int r = 0; r < AL; r++) {
-      const uint32_t* total_ptr = off + (size_t)(r + 1) * off_stride + nb;      // size of level r + 1
-      uint32_t* dst = (uint32_t*)E.aff_work[(r + 1) & 1].ptr;
-      if (r == 0)
-        k_affine_pairs<T, true><<<aff_grid, B200_AFF_THREADS, 0, s>>>(E.aff_plan[0].ptr, total_ptr, (const uint32_t*)d_points, dst, (uint4*)E.aff_scratch.ptr);
-      else
-        k_affine_pairs<T, false><<<aff_grid, B200_AFF_THREADS, 0, s>>>(E.aff_plan[r].ptr, total_ptr, (const uint32_t*)E.aff_work[r & 1].ptr, dst, (uint4*)E.aff_scratch.ptr);
-    }
-    keys = (const uint32_t*)E.keys_s.ptr;
-    vals = (const uint32_t*)E.vals_s.ptr;
-    acc_points = E.aff_work[AL & 1].ptr;
-    k_window_bounds<<<(unsigned)((nw + 1 + 63) / 64), 64, 0, s>>>(keys, acc_entries, B, nw, (unsigned long long*)E.bounds.ptr);
-    launches += 6 + AL;
-    B200_CUDA_CHECK(cudaGetLastError());
-    if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[9], s));
-  }
-  st.affine_levels = AL;
-  for (int g = 0; g < G; g++) {
-    const int w0 = g * Wg, w1 = (w0 + Wg < nw) ? w0 + Wg : nw;
-    const size_t max_slices = off0[g + 1] - off0[g];
-    // 3. accumulate (main stream)
+  cudaStream_t s = E.compute();
+  E.buckets.ensure(nbuckets * XYZZ_BYTES);
+  if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[0], s));
+  B200_CUDA_CHECK(cudaMemsetAsync(E.buckets.ptr, 0, nbuckets * XYZZ_BYTES, s));  // all-zero XYZZ = infinity
+
+  // ================= front half, once per input chunk: digits -> sort -> (batched-affine levels) -> XYZZ slices -> fix-up
+  const std::vector<InputChunk> whole = {InputChunk{0, n, wait_points}};
+  const std::vector<InputChunk>& chunks_in = input_chunks ? *input_chunks : whole;
+  for (size_t ck = 0; ck < chunks_in.size(); ck++) {
+    const InputChunk& ch = chunks_in[ck];
+    if (ch.count == 0) continue;
+    const bool into = ck > 0;                               // buckets already hold the sums of the earlier chunks
+    const bool last_chunk = ck + 1 == chunks_in.size();
+    const bool timed = E.collect_timing && last_chunk;      // phase times: those of the last (or only) chunk
+    const size_t nper = ch.count;                           // terms per MSM in this chunk (batches are never chunked)
+    const size_t ntot = batch * nper;
+    const size_t entries = (size_t)nwd * ntot;
+    const void* sc = (const char*)d_scalars + ch.begin * 32;
+    const void* pts = table_mode ? d_points : (const void*)((const char*)d_points + ch.begin * AFF_BYTES);
+    st.entries += entries;
+
+    // batched-affine levels: the XYZZ accumulation then runs over the survivor list only
+    int AL = E.tuning.affine_levels;
+    if (AL < 0) AL = auto_affine_levels(entries, nbuckets, batch);
+    if (entries >= (1ull << 31) || nbuckets >= (1ull << 30)) AL = 0;
+    if (AL > AFF_MAX_LEVELS) AL = AFF_MAX_LEVELS;
+    // level r holds sum_b ceil(n_b / 2^r) <= entries / 2^r + nbuckets slots
+    auto level_cap = [&](int r) { return (entries >> r) + nbuckets + 1; };
+    const size_t acc_entries = AL ? level_cap(AL) : entries;   // upper bound of the list k_accumulate walks
+    // slice length: about twice the mean run length (entries per bucket) so that few slices sit entirely inside one run, but
+    // never so long that the grid cannot fill the machine
+    int KACC = 32;
     {
-      dim3 block(B200_ACC_THREADS), grid((unsigned)((max_slices + B200_ACC_THREADS - 1) / B200_ACC_THREADS));
-      k_accumulate<T><<<grid, block, 0, s>>>(keys, vals, (const unsigned long long*)E.bounds.ptr, w0, w1, no_key, (const uint32_t*)acc_points,
-                                             (uint32_t*)E.buckets.ptr, (uint32_t*)E.part_pts[0].ptr + off0[g] * XW,
-                                             (uint32_t*)E.part_keys[0].ptr + off0[g], max_slices, KACC);
+      double mean_run = (double)acc_entries / (double)nbuckets;
+      while (KACC < 256 && KACC < 2.0 * mean_run && acc_entries / (size_t)(2 * KACC) >= (size_t)4 * 148 * 256) KACC *= 2;
+      if (acc_entries / 32 < (size_t)2 * 148 * 256) KACC = 16;   // fewer than two waves of slices: halve them so the SMs fill evenly
+      if (E.tuning.slice_len > 0) KACC = E.tuning.slice_len;
+    }
+    st.slice_len = KACC;
+    E.keys_a.ensure(entries * 4); E.keys_b.ensure(entries * 4);
+    E.vals_a.ensure(entries * 4); E.vals_b.ensure(entries * 4);
+    if (timed) B200_CUDA_CHECK(cudaEventRecord(E.ev[10], s));
+    // 1. digits (need the chunk's scalars only when they come over the compute stream; chunked input: wait for the chunk)
+    if (input_chunks && ch.ready) B200_CUDA_CHECK(cudaStreamWaitEvent(s, ch.ready, 0));
+    {
+      dim3 grid((unsigned)((ntot + 255) / 256)), block(256);
+      const uint32_t msm_key_stride = (uint32_t)nws * B, shared = shared_points ? 1u : 0u;
+      if (fr_mont)
+        k_digits<typename C::FrParams, true><<<grid, block, 0, s>>>((const uint32_t*)sc, (uint32_t)ntot, plan, (uint32_t*)E.keys_a.ptr, (uint32_t*)E.vals_a.ptr,
+                                                                     table_mode ? 0u : B, no_key, (uint32_t)table_stride, (uint32_t)nper, msm_key_stride, shared);
+      else
+        k_digits<typename C::FrParams, false><<<grid, block, 0, s>>>((const uint32_t*)sc, (uint32_t)ntot, plan, (uint32_t*)E.keys_a.ptr, (uint32_t*)E.vals_a.ptr,
+                                                                      table_mode ? 0u : B, no_key, (uint32_t)table_stride, (uint32_t)nper, msm_key_stride, shared);
       launches++;
     }
-    cudaStream_t q = s;
-    if (G > 1) {
-      q = E.side[g & 1];
-      B200_CUDA_CHECK(cudaEventRecord(E.ev_group[g], s));
-      B200_CUDA_CHECK(cudaStreamWaitEvent(q, E.ev_group[g], 0));
-    } else if (E.collect_timing) {
-      B200_CUDA_CHECK(cudaEventRecord(E.ev[3], s));
+    if (timed) B200_CUDA_CHECK(cudaEventRecord(E.ev[1], s));
+    // 2. sort by key
+    int end_bit = 1;
+    while ((1ull << end_bit) <= (unsigned long long)no_key) end_bit++;
+    cub::DoubleBuffer<uint32_t> dk((uint32_t*)E.keys_a.ptr, (uint32_t*)E.keys_b.ptr);
+    cub::DoubleBuffer<uint32_t> dv((uint32_t*)E.vals_a.ptr, (uint32_t*)E.vals_b.ptr);
+    {
+      size_t tmp_bytes = 0;
+      B200_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int64_t)entries, 0, end_bit, s));
+      E.cub_tmp.ensure(tmp_bytes);
+      B200_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(E.cub_tmp.ptr, tmp_bytes, dk, dv, (int64_t)entries, 0, end_bit, s));
+      launches += 2 + (end_bit + 7) / 8;  // histogram + exclusive-sum + one onesweep pass per 8 key bits
     }
-    // 4. fix-up levels of this group
+    const uint32_t* keys = dk.Current();
+    const uint32_t* vals = dv.Current();
+    if (timed) B200_CUDA_CHECK(cudaEventRecord(E.ev[2], s));
+    E.bounds.ensure((size_t)(nw + 1) * 8);
+    k_window_bounds<<<(unsigned)((nw + 1 + 63) / 64), 64, 0, s>>>(keys, entries, B, nw, (unsigned long long*)E.bounds.ptr);
+    launches++;
+    // slices (upper bounds known on the host; the exact entry ranges stay on the device)
+    size_t max_slices;
+    {
+      size_t set_cap = table_mode ? (size_t)nwd * nper : nper;   // a bucket set holds <= n (table: nwd * n) entries
+      if (AL) set_cap = (set_cap >> AL) + B + 1;                 // ... of which ceil(run / 2^AL) per bucket survive the affine levels
+      max_slices = ((size_t)nw * set_cap + KACC - 1) / KACC;
+    }
+    const size_t max_fix = (max_slices + KFIX - 1) / KFIX;
+    E.part_pts[0].ensure(max_slices * XYZZ_BYTES); E.part_keys[0].ensure(max_slices * 4);
+    E.part_pts[1].ensure(max_fix * XYZZ_BYTES); E.part_keys[1].ensure(max_fix * 4);
+    // points of a chunked / host call arrive on the copy stream
+    if (!input_chunks && ch.ready) B200_CUDA_CHECK(cudaStreamWaitEvent(s, ch.ready, 0));
+    const void* acc_points = pts;
+    if (AL) {
+      const uint32_t nb = (uint32_t)nbuckets;
+      const uint32_t nblk = (nb + SCAN_ITEMS - 1) / SCAN_ITEMS;
+      const size_t off_stride = (size_t)nb + 1;
+      E.aff_head.ensure((size_t)nb * 4); E.aff_tail.ensure((size_t)nb * 4);
+      E.aff_off.ensure((size_t)(AL + 1) * off_stride * 4);
+      E.aff_blocksum.ensure((size_t)(AL + 1) * nblk * 4);
+      E.aff_plan[0].ensure(level_cap(1) * 8);
+      for (int r = 1; r < AL; r++) E.aff_plan[r].ensure(level_cap(r + 1) * 4);
+      E.aff_work[1].ensure(level_cap(1) * AFF_BYTES);               // odd levels
+      if (AL >= 2) E.aff_work[0].ensure(level_cap(2) * AFF_BYTES);  // even levels
+      E.keys_s.ensure(acc_entries * 4);
+      E.vals_s.ensure(acc_entries * 4);
+      // persistent grid of the pair kernel: as many blocks as stay resident
+      int bps = 0;
+      B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_affine_pairs<T, true>, B200_AFF_THREADS, 0));
+      int bps2 = 0;
+      B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps2, k_affine_pairs<T, false>, B200_AFF_THREADS, 0));
+      if (bps2 < bps) bps = bps2;
+      if (bps < 1) bps = 1;
+      const unsigned aff_grid = (unsigned)(E.sm_count * bps);
+      const size_t aff_threads = (size_t)aff_grid * B200_AFF_THREADS;
+      const size_t per_thread = (level_cap(1) + aff_threads - 1) / aff_threads;
+      E.aff_scratch.ensure(per_thread * aff_threads * (size_t)T::WORDS * 4);
+      uint32_t* head = (uint32_t*)E.aff_head.ptr;
+      uint32_t* tail = (uint32_t*)E.aff_tail.ptr;
+      uint32_t* off = (uint32_t*)E.aff_off.ptr;
+      B200_CUDA_CHECK(cudaMemsetAsync(head, 0, (size_t)nb * 4, s));
+      B200_CUDA_CHECK(cudaMemsetAsync(tail, 0, (size_t)nb * 4, s));
+      B200_CUDA_CHECK(cudaMemsetAsync(E.keys_s.ptr, 0xFF, acc_entries * 4, s));   // KEY_NONE: the unused tail sorts last, like zero digits
+      const unsigned eb = (unsigned)((entries + 255) / 256);
+      k_bucket_bounds<<<eb, 256, 0, s>>>(keys, entries, no_key, head, tail);
+      k_level_blocksums<<<nblk, SCAN_THREADS, 0, s>>>(head, tail, nb, AL, nblk, (uint32_t*)E.aff_blocksum.ptr);
+      k_level_scan<<<1, SCAN_THREADS, 0, s>>>((uint32_t*)E.aff_blocksum.ptr, nblk, AL, nb, off);
+      k_level_offsets<<<nblk, SCAN_THREADS, 0, s>>>(head, tail, nb, AL, nblk, (const uint32_t*)E.aff_blocksum.ptr, off);
+      AffinePlan aplan;
+      aplan.plan0 = (uint2*)E.aff_plan[0].ptr;
+      for (int r = 0; r < AFF_MAX_LEVELS; r++) aplan.plan[r] = (r >= 1 && r < AL) ? (uint32_t*)E.aff_plan[r].ptr : nullptr;
+      aplan.surv_keys = (uint32_t*)E.keys_s.ptr;
+      aplan.surv_vals = (uint32_t*)E.vals_s.ptr;
+      k_affine_plan<<<eb, 256, 0, s>>>(keys, vals, entries, no_key, head, tail, off, nb, AL, aplan);
+      for (int r = 0; r < AL; r++) {
+        const uint32_t* total_ptr = off + (size_t)(r + 1) * off_stride + nb;      // size of level r + 1
+        uint32_t* dst = (uint32_t*)E.aff_work[(r + 1) & 1].ptr;
+        if (r == 0)
+          k_affine_pairs<T, true><<<aff_grid, B200_AFF_THREADS, 0, s>>>(E.aff_plan[0].ptr, total_ptr, (const uint32_t*)pts, dst, (uint4*)E.aff_scratch.ptr);
+        else
+          k_affine_pairs<T, false><<<aff_grid, B200_AFF_THREADS, 0, s>>>(E.aff_plan[r].ptr, total_ptr, (const uint32_t*)E.aff_work[r & 1].ptr, dst, (uint4*)E.aff_scratch.ptr);
+      }
+      keys = (const uint32_t*)E.keys_s.ptr;
+      vals = (const uint32_t*)E.vals_s.ptr;
+      acc_points = E.aff_work[AL & 1].ptr;
+      k_window_bounds<<<(unsigned)((nw + 1 + 63) / 64), 64, 0, s>>>(keys, acc_entries, B, nw, (unsigned long long*)E.bounds.ptr);
+      launches += 6 + AL;
+      B200_CUDA_CHECK(cudaGetLastError());
+      if (timed) B200_CUDA_CHECK(cudaEventRecord(E.ev[9], s));
+    }
+    st.affine_levels = AL;
+    // 3. accumulate
+    {
+      dim3 block(B200_ACC_THREADS), grid((unsigned)((max_slices + B200_ACC_THREADS - 1) / B200_ACC_THREADS));
+      k_accumulate<T><<<grid, block, 0, s>>>(keys, vals, (const unsigned long long*)E.bounds.ptr, 0, nw, no_key, (const uint32_t*)acc_points,
+                                             (uint32_t*)E.buckets.ptr, (uint32_t*)E.part_pts[0].ptr, (uint32_t*)E.part_keys[0].ptr, max_slices, KACC,
+                                             into ? 1 : 0);
+      launches++;
+    }
+    if (timed) B200_CUDA_CHECK(cudaEventRecord(E.ev[3], s));
+    // 4. fix-up levels
     {
       size_t count = max_slices;
       int cur = 0;
       while (count > 1) {
         size_t ns = (count + KFIX - 1) / KFIX;
         dim3 block(128), grid((unsigned)((count + 127) / 128));
-        const size_t oin = cur ? off1[g] : off0[g], oout = cur ? off0[g] : off1[g];
-        k_fixup<T><<<grid, block, 0, q>>>((const uint32_t*)E.part_keys[cur].ptr + oin, (const uint32_t*)E.part_pts[cur].ptr + oin * XW, count,
-                                          (uint32_t*)E.buckets.ptr, (uint32_t*)E.part_pts[cur ^ 1].ptr + oout * XW,
-                                          (uint32_t*)E.part_keys[cur ^ 1].ptr + oout);
+        k_fixup<T><<<grid, block, 0, s>>>((const uint32_t*)E.part_keys[cur].ptr, (const uint32_t*)E.part_pts[cur].ptr, count,
+                                          (uint32_t*)E.buckets.ptr, (uint32_t*)E.part_pts[cur ^ 1].ptr, (uint32_t*)E.part_keys[cur ^ 1].ptr);
         launches++;
         count = ns;
         cur ^= 1;
       }
       // the last level is a single chunk: its first entry has no predecessor, so nothing is forwarded any further
     }
-    if (G == 1 && E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[4], s));
-    // 5. bucket reduce of this group's windows: chunked running sums, offsets, warp-butterfly row sums (<= 4 per window left)
-    {
-      const uint32_t nwg = (uint32_t)(w1 - w0);
-      size_t threads = (size_t)chunks * nwg;
-      dim3 block(64), grid((unsigned)((threads + 63) / 64));
-      uint32_t* ra = (uint32_t*)E.red_a.ptr + (size_t)w0 * chunks * XW;
-      uint32_t* rb = (uint32_t*)E.red_b.ptr + (size_t)w0 * chunks * XW;
-      k_bucket_reduce<T, INL><<<grid, block, 0, q>>>((const uint32_t*)E.buckets.ptr + (size_t)w0 * B * XW, B, L, chunks, nwg, ra, rb);
-      k_chunk_offset<T, INL><<<grid, block, 0, q>>>(ra, rb, L, chunks, nwg, nbits);
-      launches += 2;
-      uint32_t row = chunks;
-      bool in_a = true;
-      // single MSM: <= 4 partial sums per window go to the host tail; batch: down to one, the device tail is a serial chain
-      const uint32_t row_stop = batch > 1 ? 1u : 4u;
-      while (row > row_stop) {
-        uint32_t out_row = (row + 31) / 32;
-        size_t warps = (size_t)out_row * nwg;
-        dim3 blk(128), grd((unsigned)((warps * 32 + 127) / 128));
-        // rows of a level live at window-major offsets computed with that level's row length
-        const uint32_t* in = (const uint32_t*)(in_a ? E.red_a.ptr : E.red_b.ptr) + (size_t)w0 * row * XW;
-        uint32_t* out = (uint32_t*)(in_a ? E.red_b.ptr : E.red_a.ptr) + (size_t)w0 * out_row * XW;
-        k_row_sum_warp<T, INL><<<grd, blk, 0, q>>>(in, row, out_row, nwg, out);
-        launches++;
-        row = out_row;
-        in_a = !in_a;
-      }
-      row_final = row;
-      final_in_a = in_a;
+    if (timed) B200_CUDA_CHECK(cudaEventRecord(E.ev[4], s));
+  }
+
+  // ================= back half, once: bucket reduction and tail
+  // bit-plane reduction (single MSMs): buckets as a 2^rbits x 2^a matrix per window, see k_rowcol_sums
+  const bool plane_reduce = (batch == 1 && E.tuning.reduce_mode == 0);
+  const int pr_a = (c - 1) / 2, pr_rbits = (c - 1) - pr_a;
+  const uint32_t pr_planes = (uint32_t)c;                       // rbits + a + 1 partial points per window
+  uint32_t row = 0;
+  DeviceBuffer* src = &E.red_a;
+  if (plane_reduce) {
+    const uint32_t Cn = 1u << pr_a, Rn = 1u << pr_rbits;
+    // terms summed serially by one lane: as many as keep >= ~8 warps per SM busy, at least 2
+    const size_t want_threads = (size_t)E.sm_count * 256;
+    uint32_t serial = 2;
+    while (serial < 64 && nbuckets / (size_t)serial >= want_threads) serial *= 2;
+    auto lanes_for = [&](uint32_t len) { uint32_t l = len / serial; if (l < 1) l = 1; if (l > 32) l = 32; return (int)l; };
+    const int lanes_r = lanes_for(Cn), lanes_c = lanes_for(Rn);
+    E.red_a.ensure((size_t)nw * Rn * XYZZ_BYTES);
+    E.red_b.ensure((size_t)nw * Cn * XYZZ_BYTES);
+    E.red_planes.ensure((size_t)nw * pr_planes * XYZZ_BYTES);
+    // row sums + column sums of every window, then the bit planes: c partial points per window for the host tail
+    const size_t tr = (size_t)nw * Rn * lanes_r, tc = (size_t)nw * Cn * lanes_c;
+    k_rowcol_sums<T, INL, false><<<(unsigned)((tr + 127) / 128), 128, 0, s>>>((const uint32_t*)E.buckets.ptr, B, pr_a, (uint32_t)nw, lanes_r,
+                                                                              (uint32_t*)E.red_a.ptr);
+    k_rowcol_sums<T, INL, true><<<(unsigned)((tc + 127) / 128), 128, 0, s>>>((const uint32_t*)E.buckets.ptr, B, pr_a, (uint32_t)nw, lanes_c,
+                                                                             (uint32_t*)E.red_b.ptr);
+    const size_t tp = (size_t)nw * pr_planes * 32;
+    k_plane_sums<T, INL><<<(unsigned)((tp + 127) / 128), 128, 0, s>>>((const uint32_t*)E.red_a.ptr, (const uint32_t*)E.red_b.ptr, pr_a, pr_rbits,
+                                                                      (uint32_t)nw, (uint32_t*)E.red_planes.ptr);
+    launches += 3;
+  } else {
+    // running-sum chunks, offsets, warp-butterfly row sums (<= 4 per window left; batches: one)
+    uint32_t L = (uint32_t)E.tuning.reduce_chunk;
+    if (L < 1) L = 1;
+    uint32_t chunks = (B + L - 1) / L;
+    // small bucket counts: the phase is a chain of dependent point operations, so trade chunk length for more threads
+    // (a larger target for Fp2 was measured slower: the offset multiplication per chunk dominates then)
+    const size_t want_threads = (size_t)E.sm_count * 64;
+    while (L > 1 && (size_t)chunks * nw < want_threads && chunks < B) { L = (L + 1) / 2; chunks = (B + L - 1) / L; }
+    int nbits = 0;
+    while (nbits < 32 && ((uint64_t)(chunks - 1) * L >> nbits) != 0) nbits++;
+    E.red_a.ensure((size_t)chunks * nw * XYZZ_BYTES);
+    E.red_b.ensure((size_t)chunks * nw * XYZZ_BYTES);
+    size_t threads = (size_t)chunks * nw;
+    dim3 block(64), grid((unsigned)((threads + 63) / 64));
+    k_bucket_reduce<T, INL><<<grid, block, 0, s>>>((const uint32_t*)E.buckets.ptr, B, L, chunks, (uint32_t)nw, (uint32_t*)E.red_a.ptr, (uint32_t*)E.red_b.ptr);
+    k_chunk_offset<T, INL><<<grid, block, 0, s>>>((uint32_t*)E.red_a.ptr, (const uint32_t*)E.red_b.ptr, L, chunks, (uint32_t)nw, nbits);
+    launches += 2;
+    row = chunks;
+    bool in_a = true;
+    // single MSM: <= 4 partial sums per window go to the host tail; batch: down to one, the device tail is a serial chain
+    const uint32_t row_stop = batch > 1 ? 1u : 4u;
+    while (row > row_stop) {
+      uint32_t out_row = (row + 31) / 32;
+      size_t warps = (size_t)out_row * nw;
+      dim3 blk(128), grd((unsigned)((warps * 32 + 127) / 128));
+      k_row_sum_warp<T, INL><<<grd, blk, 0, s>>>((const uint32_t*)(in_a ? E.red_a.ptr : E.red_b.ptr), row, out_row, (uint32_t)nw,
+                                                 (uint32_t*)(in_a ? E.red_b.ptr : E.red_a.ptr));
+      launches++;
+      row = out_row;
+      in_a = !in_a;
     }
-    if (G > 1) B200_CUDA_CHECK(cudaEventRecord(E.ev_side[g & 1], q));
+    src = in_a ? &E.red_a : &E.red_b;
   }
-  if (G > 1) {
-    if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[3], s));   // end of the last accumulate
-    B200_CUDA_CHECK(cudaStreamWaitEvent(s, E.ev_side[0], 0));
-    B200_CUDA_CHECK(cudaStreamWaitEvent(s, E.ev_side[1], 0));
-    if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[4], s));
-  }
-  const uint32_t row = row_final;
-  DeviceBuffer* src = final_in_a ? &E.red_a : &E.red_b;
   if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[5], s));
   static_assert(sizeof(HP) == XYZZ_BYTES, "host/device XYZZ layout");
+  auto read_times = [&]() {
+    if (!E.collect_timing) return;
+    B200_CUDA_CHECK(cudaEventRecord(E.ev[6], s));
+    B200_CUDA_CHECK(cudaEventSynchronize(E.ev[6]));
+    cudaEventElapsedTime(&st.ms_digits, E.ev[10], E.ev[1]);
+    cudaEventElapsedTime(&st.ms_sort, E.ev[1], E.ev[2]);
+    cudaEventElapsedTime(&st.ms_accumulate, E.ev[2], E.ev[3]);
+    if (st.affine_levels) cudaEventElapsedTime(&st.ms_affine, E.ev[2], E.ev[9]);
+    cudaEventElapsedTime(&st.ms_fixup, E.ev[3], E.ev[4]);
+    cudaEventElapsedTime(&st.ms_reduce, E.ev[4], E.ev[5]);
+    cudaEventElapsedTime(&st.ms_d2h_tail, E.ev[5], E.ev[6]);
+    cudaEventElapsedTime(&st.ms_total, E.ev[0], E.ev[6]);
+  };
   if (batch > 1) {
     // 6b. batch: partial sums + Horner per MSM on the device (one thread per MSM), then `batch` points -> host
-    DeviceBuffer* dst = final_in_a ? &E.red_b : &E.red_a;   // the other reduce buffer is free by now (>= nw points)
+    DeviceBuffer* dst = (src == &E.red_a) ? &E.red_b : &E.red_a;   // the other reduce buffer is free by now (>= nw points)
     k_batch_tail<T><<<(unsigned)((batch + 63) / 64), 64, 0, s>>>((const uint32_t*)src->ptr, row, nws, c, (uint32_t)batch, (uint32_t*)dst->ptr);
     launches++;
     E.ensure_host(batch * XYZZ_BYTES);
     B200_CUDA_CHECK(cudaMemcpyAsync(E.h_result, dst->ptr, batch * XYZZ_BYTES, cudaMemcpyDeviceToHost, s));
     B200_CUDA_CHECK(cudaStreamSynchronize(s));
     memcpy((void*)batch_out, E.h_result, batch * XYZZ_BYTES);
-    if (E.collect_timing) {
-      B200_CUDA_CHECK(cudaEventRecord(E.ev[6], s));
-      B200_CUDA_CHECK(cudaEventSynchronize(E.ev[6]));
-      cudaEventElapsedTime(&st.ms_digits, E.ev[0], E.ev[1]);
-      cudaEventElapsedTime(&st.ms_sort, E.ev[1], E.ev[2]);
-      cudaEventElapsedTime(&st.ms_accumulate, E.ev[2], E.ev[3]);
-      if (AL) cudaEventElapsedTime(&st.ms_affine, E.ev[2], E.ev[9]);
-      cudaEventElapsedTime(&st.ms_fixup, E.ev[3], E.ev[4]);
-      cudaEventElapsedTime(&st.ms_reduce, E.ev[4], E.ev[5]);
-      cudaEventElapsedTime(&st.ms_d2h_tail, E.ev[5], E.ev[6]);
-      cudaEventElapsedTime(&st.ms_total, E.ev[0], E.ev[6]);
-    }
+    read_times();
     st.kernel_launches = launches;
     return HP::inf();
   }
-  // 6. per-window partial sums (<= 4 each) -> host; finish the sums and run the Horner tail there
-  const size_t out_bytes = (size_t)nw * row * XYZZ_BYTES;
-  E.ensure_host(out_bytes);
-  B200_CUDA_CHECK(cudaMemcpyAsync(E.h_result, src->ptr, out_bytes, cudaMemcpyDeviceToHost, s));
-  B200_CUDA_CHECK(cudaStreamSynchronize(s));
-  const HP* parts = reinterpret_cast<const HP*>(E.h_result);
-  auto window_sum = [&](int w) {
-    HP a = parts[(size_t)w * row];
-    for (uint32_t i = 1; i < row; i++) a = host::xyzz_add(a, parts[(size_t)w * row + i]);
-    return a;
-  };
-  // r = sum_w 2^(c*w) S_w  for w in [win_begin, win_end):  Horner from the top window of the range, then shift by c*win_begin
-  // (reference ec_multi_scalar_mul_parallel.nim:198-203: c doublings + one addition per window).
-  HP r = window_sum(nw - 1);
-  for (int w = nw - 2; w >= 0; w--) {
-    for (int i = 0; i < c; i++) r = host::xyzz_dbl(r);
-    r = host::xyzz_add(r, window_sum(w));
+  // 6. host tail. r = sum_w 2^(c*w) S_w  for w in [win_begin, win_end): Horner over the bit positions (reference
+  // ec_multi_scalar_mul_parallel.nim:198-203: c doublings + one addition per window), including the shift by c*win_begin.
+  HP r = HP::inf();
+  if (plane_reduce) {
+    // window w arrives as c partial points with S_w = sum_p 2^e(p) P_p: e = a + p for the row planes, p - rbits for the column
+    // planes; one doubling per bit position, one addition per non-empty position
+    const size_t out_bytes = (size_t)nw * pr_planes * XYZZ_BYTES;
+    E.ensure_host(out_bytes);
+    B200_CUDA_CHECK(cudaMemcpyAsync(E.h_result, E.red_planes.ptr, out_bytes, cudaMemcpyDeviceToHost, s));
+    B200_CUDA_CHECK(cudaStreamSynchronize(s));
+    const HP* parts = reinterpret_cast<const HP*>(E.h_result);
+    const int wshift = table_mode ? 0 : plan.win_begin;
+    const int emax = c * (wshift + nw - 1) + (c - 1);
+    static thread_local std::vector<HP> by_exp;
+    by_exp.assign((size_t)emax + 1, HP::inf());
+    for (int w = 0; w < nw; w++)
+      for (uint32_t p = 0; p < pr_planes; p++) {
+        const HP& pt = parts[(size_t)w * pr_planes + p];
+        if (pt.is_inf()) continue;
+        const int e = c * (wshift + w) + ((int)p < pr_rbits ? pr_a + (int)p : (int)p - pr_rbits);
+        by_exp[e] = host::xyzz_add(by_exp[e], pt);
+      }
+    for (int e = emax; e >= 0; e--) {
+      r = host::xyzz_dbl(r);
+      if (!by_exp[e].is_inf()) r = host::xyzz_add(r, by_exp[e]);
+    }
+  } else {
+    // per-window partial sums (<= 4 each) -> host; finish the sums there
+    const size_t out_bytes = (size_t)nw * row * XYZZ_BYTES;
+    E.ensure_host(out_bytes);
+    B200_CUDA_CHECK(cudaMemcpyAsync(E.h_result, src->ptr, out_bytes, cudaMemcpyDeviceToHost, s));
+    B200_CUDA_CHECK(cudaStreamSynchronize(s));
+    const HP* parts = reinterpret_cast<const HP*>(E.h_result);
+    auto window_sum = [&](int w) {
+      HP a = parts[(size_t)w * row];
+      for (uint32_t i = 1; i < row; i++) a = host::xyzz_add(a, parts[(size_t)w * row + i]);
+      return a;
+    };
+    r = window_sum(nw - 1);
+    for (int w = nw - 2; w >= 0; w--) {
+      for (int i = 0; i < c; i++) r = host::xyzz_dbl(r);
+      r = host::xyzz_add(r, window_sum(w));
+    }
+    for (int i = 0; i < c * plan.win_begin; i++) r = host::xyzz_dbl(r);
   }
-  for (int i = 0; i < c * plan.win_begin; i++) r = host::xyzz_dbl(r);
-  if (E.collect_timing) {
-    B200_CUDA_CHECK(cudaEventRecord(E.ev[6], s));
-    B200_CUDA_CHECK(cudaEventSynchronize(E.ev[6]));
-    cudaEventElapsedTime(&st.ms_digits, E.ev[0], E.ev[1]);
-    cudaEventElapsedTime(&st.ms_sort, E.ev[1], E.ev[2]);
-    cudaEventElapsedTime(&st.ms_accumulate, E.ev[2], E.ev[3]);
-    if (AL) cudaEventElapsedTime(&st.ms_affine, E.ev[2], E.ev[9]);
-    cudaEventElapsedTime(&st.ms_fixup, E.ev[3], E.ev[4]);
-    cudaEventElapsedTime(&st.ms_reduce, E.ev[4], E.ev[5]);
-    cudaEventElapsedTime(&st.ms_d2h_tail, E.ev[5], E.ev[6]);
-    cudaEventElapsedTime(&st.ms_total, E.ev[0], E.ev[6]);
-  }
+  read_times();
   st.kernel_launches = launches;
   return r;
 }
@@ -698,13 +734,32 @@ host::HXyzz<typename C::H> msm_host_on(int device, const void* coefs, const void
   E.d_points.ensure(pbytes);
   cudaEvent_t t0 = E.ev[7], t1 = E.ev[8];
   B200_CUDA_CHECK(cudaEventRecord(t0, E.compute()));
-  // scalars on the compute stream (digits + sort need only them); points on the copy stream so that the transfer
-  // overlaps digit extraction and sorting.
-  B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, sbytes, cudaMemcpyHostToDevice, E.compute()));
-  B200_CUDA_CHECK(cudaMemcpyAsync(E.d_points.ptr, points, pbytes, cudaMemcpyHostToDevice, E.copy_stream));
-  B200_CUDA_CHECK(cudaEventRecord(E.ev_points_ready, E.copy_stream));
-  B200_CUDA_CHECK(cudaEventRecord(t1, E.compute()));
-  HP r = msm_device<C>(E, E.d_scalars.ptr, E.d_points.ptr, len, fr_mont, 0, 0, -1, E.ev_points_ready);
+  // Large inputs cross PCIe in a few chunks (scalars and points of chunk k, then chunk k+1, all on the copy stream) and the
+  // engine starts on chunk k as soon as it has landed: only the first chunk's transfer is exposed. Small inputs go in one
+  // piece: scalars on the compute stream (digits + sort need only them), points on the copy stream beside them.
+  int P = E.tuning.input_chunks;
+  if (P <= 0) P = len >= (1u << 19) ? 4 : (len >= (1u << 17) ? 2 : 1);
+  if (P > Engine::MAX_INPUT_CHUNKS) P = Engine::MAX_INPUT_CHUNKS;
+  HP r;
+  if (P > 1) {
+    std::vector<InputChunk> chunks((size_t)P);
+    const size_t pt = 2 * (size_t)C::COORD_BYTES;
+    for (int k = 0; k < P; k++) {
+      const size_t lo = len * (size_t)k / (size_t)P, hi = len * (size_t)(k + 1) / (size_t)P;
+      chunks[k] = InputChunk{lo, hi - lo, E.ev_chunk[k]};
+      B200_CUDA_CHECK(cudaMemcpyAsync((char*)E.d_scalars.ptr + lo * 32, (const char*)coefs + lo * 32, (hi - lo) * 32, cudaMemcpyHostToDevice, E.copy_stream));
+      B200_CUDA_CHECK(cudaMemcpyAsync((char*)E.d_points.ptr + lo * pt, (const char*)points + lo * pt, (hi - lo) * pt, cudaMemcpyHostToDevice, E.copy_stream));
+      B200_CUDA_CHECK(cudaEventRecord(E.ev_chunk[k], E.copy_stream));
+    }
+    B200_CUDA_CHECK(cudaEventRecord(t1, E.compute()));
+    r = msm_device<C>(E, E.d_scalars.ptr, E.d_points.ptr, len, fr_mont, 0, 0, -1, nullptr, 0, 1, false, nullptr, &chunks);
+  } else {
+    B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, sbytes, cudaMemcpyHostToDevice, E.compute()));
+    B200_CUDA_CHECK(cudaMemcpyAsync(E.d_points.ptr, points, pbytes, cudaMemcpyHostToDevice, E.copy_stream));
+    B200_CUDA_CHECK(cudaEventRecord(E.ev_points_ready, E.copy_stream));
+    B200_CUDA_CHECK(cudaEventRecord(t1, E.compute()));
+    r = msm_device<C>(E, E.d_scalars.ptr, E.d_points.ptr, len, fr_mont, 0, 0, -1, E.ev_points_ready);
+  }
   if (E.collect_timing) cudaEventElapsedTime(&E.stats.ms_h2d, t0, t1);
   if (stats_out) *stats_out = E.stats;
   return r;

@@ -114,6 +114,7 @@ constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 // the same warp through shared memory and added into that lane's last run before it is stored (one extra XYZZ add per
 // warp), so only heads whose predecessor lives in another warp -- or is itself a single-run continuation slice --
 // are spilled to the global partial list that k_fixup resolves.
+// `into` != 0: the buckets already hold sums (earlier input chunks of the same MSM, msm_engine.cuh) and this launch adds to them.
 #ifndef B200_ACC_MIN_BLOCKS
 #define B200_ACC_MIN_BLOCKS 2
 #endif
@@ -124,7 +125,7 @@ template <class T>
 __global__ void __launch_bounds__(B200_ACC_THREADS, (T::WORDS <= 12) ? B200_ACC_MIN_BLOCKS : 1)
 k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const unsigned long long* __restrict__ bounds,
              int w0, int w1, uint32_t no_key, const uint32_t* __restrict__ points, uint32_t* buckets, uint32_t* part_pts,
-             uint32_t* part_keys, size_t max_slices, int K) {
+             uint32_t* part_keys, size_t max_slices, int K, int into) {
   // entries of windows [w0, w1) occupy sorted positions [begin, total); slices are counted from `begin`
   const size_t begin = (size_t)bounds[w0], total = (size_t)bounds[w1];
   const size_t num_slices = (total - begin + (size_t)K - 1) / (size_t)K;
@@ -162,11 +163,14 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
           else store_xyzz(buckets, (size_t)cur_key, acc);
           first_run = false;
         }
+        // a run this thread owns starts from the bucket's current value when earlier input chunks already accumulated into
+        // the buckets (`into`), from infinity otherwise; a run continuing the previous slice ("head") always starts from infinity
+        const bool owned = !(first_run && key == prev_key);
         cur_key = key;
-        acc = Xyzz<T>::from_affine(p);
-      } else {
-        xyzz_madd(acc, p);
+        if (into && owned) acc = load_xyzz<T>(buckets, (size_t)key);
+        else acc = Xyzz<T>::inf();
       }
+      xyzz_madd(acc, p);   // onto infinity: a copy
     }
   }
   // the last run of the slice is still in `acc`
@@ -350,6 +354,91 @@ __global__ void __launch_bounds__(128) k_row_sum_warp(const uint32_t* in, uint32
     padd<T, INL>(acc, other);
   }
   if (lane == 0) store_xyzz(out, warp, acc);
+}
+
+// ------------------------------------------------------------------------------------------- bucket reduction, bit-plane form
+// Same window sum  S = sum_j (j+1) * bucket[j]  (reference ec_multi_scalar_mul.nim:186-197), reorganised so that no thread
+// walks a long chain of dependent point additions (the running-sum form above needs ~2L + log2(B) of them):
+//   view the B = 2^(c-1) buckets of a window as a matrix of R = 2^rbits rows and C = 2^a columns, j = h*C + l, so that
+//   j + 1 = h*C + (l + 1)  and   S = C * sum_h h*H_h + sum_l (l+1)*L_l   with the row sums H_h and the column sums L_l;
+//   a sum  sum_i i*X_i  over 2^k points is  sum_b 2^b * (sum of the X_i whose index has bit b set): "bit planes".
+//   k_rowcol_sums: every row sum and every column sum, `lanes` lanes per sum (strided serial part + xor butterfly);
+//   k_plane_sums : one warp per (window, plane): rbits planes of H (bits of h), a+1 planes of L (bits of l+1).
+// A window leaves the device as c partial points P_e with  S = sum_e 2^e P_e; the host tail folds the 2^e into the
+// Horner evaluation over the windows it runs anyway (one doubling per bit position, one addition per partial point).
+// Work: 2 additions per bucket as before, but the longest dependent chain is C/lanes + R/lanes + 2 log2(lanes) + ~13
+// additions instead of ~66, and every stage is a plain sum (any number of lanes per sum).
+template <class T, bool INL>
+B200_DEV void group_butterfly(Xyzz<T>& acc, int lanes) {
+#pragma unroll 1
+  for (int d = lanes >> 1; d >= 1; d >>= 1) {
+    Xyzz<T> other;
+#pragma unroll
+    for (int k = 0; k < T::WORDS; k++) {
+      other.x.set_word(k, __shfl_xor_sync(0xFFFFFFFFu, acc.x.word(k), d));
+      other.y.set_word(k, __shfl_xor_sync(0xFFFFFFFFu, acc.y.word(k), d));
+      other.zz.set_word(k, __shfl_xor_sync(0xFFFFFFFFu, acc.zz.word(k), d));
+      other.zzz.set_word(k, __shfl_xor_sync(0xFFFFFFFFu, acc.zzz.word(k), d));
+    }
+    padd<T, INL>(acc, other);
+  }
+}
+
+// COLS = false: out[w*R + h] = sum_l bucket[w][h*C + l];  COLS = true: out[w*C + l] = sum_h bucket[w][h*C + l].
+// `lanes` (power of two <= 32) lanes share one sum; the grid is a whole number of warps and every lane reaches the shuffles.
+template <class T, bool INL, bool COLS>
+__global__ void __launch_bounds__(128) k_rowcol_sums(const uint32_t* buckets, uint32_t buckets_per_window, int a, uint32_t num_windows,
+                                                     int lanes, uint32_t* out) {
+  const uint32_t C = 1u << a, R = buckets_per_window >> a;
+  const uint32_t per_window = COLS ? C : R;                 // sums per window
+  const uint32_t len = COLS ? R : C;                        // terms per sum
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t sum_id = g / (unsigned)lanes;
+  const uint32_t t = (uint32_t)(g % (unsigned)lanes);
+  const bool live = sum_id < (size_t)per_window * num_windows;
+  Xyzz<T> acc = Xyzz<T>::inf();
+  if (live) {
+    const uint32_t w = (uint32_t)(sum_id / per_window), i = (uint32_t)(sum_id % per_window);
+    const size_t base = (size_t)w * buckets_per_window;
+#pragma unroll 1
+    for (uint32_t k = t; k < len; k += (uint32_t)lanes) {
+      const size_t j = COLS ? ((size_t)k * C + i) : ((size_t)i * C + k);
+      Xyzz<T> b = load_xyzz<T>(buckets, base + j);
+      padd<T, INL>(acc, b);
+    }
+  }
+  group_butterfly<T, INL>(acc, lanes);
+  if (live && t == 0) store_xyzz(out, sum_id, acc);
+}
+
+// One warp per (window w, plane p): p < rbits: H plane (bit p of the row index h); p >= rbits: L plane b = p - rbits
+// (bit b of l + 1).  out[w * (rbits + a + 1) + p].
+template <class T, bool INL>
+__global__ void __launch_bounds__(128) k_plane_sums(const uint32_t* row_sums, const uint32_t* col_sums, int a, int rbits,
+                                                    uint32_t num_windows, uint32_t* out) {
+  const unsigned lane = threadIdx.x & 31u;
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t planes = (uint32_t)(rbits + a + 1);
+  const bool live = warp < (size_t)planes * num_windows;
+  Xyzz<T> acc = Xyzz<T>::inf();
+  if (live) {
+    const uint32_t w = (uint32_t)(warp / planes), p = (uint32_t)(warp % planes);
+    const bool is_h = p < (uint32_t)rbits;
+    const uint32_t bit = is_h ? p : p - (uint32_t)rbits;
+    const uint32_t len = is_h ? (1u << rbits) : (1u << a);
+    const uint32_t* src = is_h ? row_sums : col_sums;
+    const size_t base = (size_t)w * len;
+#pragma unroll 1
+    for (uint32_t i = lane; i < len; i += 32u) {
+      const uint32_t weight = is_h ? i : i + 1u;
+      if ((weight >> bit) & 1u) {
+        Xyzz<T> b = load_xyzz<T>(src, base + i);
+        padd<T, INL>(acc, b);
+      }
+    }
+  }
+  group_butterfly<T, INL>(acc, 32);
+  if (live && lane == 0) store_xyzz(out, warp, acc);
 }
 
 // Batch tail: one thread per MSM of a batch. parts[(m * nwd + w) * row + i] are the <= 4 partial sums of window w of

@@ -468,3 +468,66 @@ def test_caller_thread_with_another_current_device(M, lib, tp, oracle_lib):
     t.join()
     assert out["got"] == want
     assert out["dev_after"] == other          # the caller's current device is restored
+
+
+# ------------------------------------------------------------------ engine modes that must not change the result
+@pytest.mark.parametrize("curve,n", [("bls12_381_g1", 70001), ("bn254_snarks_g1", 4099), ("bls12_381_g2", 2500), ("pallas_ec", 33)])
+def test_input_chunks_and_reduce_modes_same_result(M, lib, tp, oracle_lib, curve, n):
+    """ctt_b200_set_input_chunks (the host input crosses PCIe in k chunks that accumulate into the same buckets) x
+    ctt_b200_set_reduce_mode (bit-plane / running-sum bucket reduction) x forced batched-affine levels: every combination
+    returns the oracle's group element. Few distinct points, so equal points meet inside and across chunks."""
+    cv = CURVES[curve]
+    rnd = random.Random(n)
+    _, pool = point_pool(cv)
+    pts = [pool[rnd.randrange(10)] for _ in range(n)]
+    ks = [rnd.getrandbits(cv.scalar_bits) for _ in range(n)]
+    if n > 40:
+        pts[11] = None
+        ks[12] = 0
+        ks[13] = ks[14] = 1                      # P and P again: a doubling inside a bucket
+        pts[13] = pts[14]
+    cb, pb = pack(cv, ks, pts)
+    want = pyref.jac_bytes_to_affine(oracle_lib.msm(cv, cb, pb, n), cv)
+    try:
+        for chunks in (1, 2, 3, 5, 8):
+            for mode in (0, 1):
+                for levels in (-1, 0, 2):
+                    lib.ctt_b200_set_input_chunks(chunks)
+                    lib.ctt_b200_set_reduce_mode(mode)
+                    lib.ctt_b200_set_affine_levels(levels)
+                    got = M.multi_scalar_mul_vartime_parallel(tp, cv, cb, pb, n)
+                    assert pyref.jac_bytes_to_affine(got, cv) == want, (curve, chunks, mode, levels)
+    finally:
+        lib.ctt_b200_set_input_chunks(0)
+        lib.ctt_b200_set_reduce_mode(0)
+        lib.ctt_b200_set_affine_levels(-1)
+
+
+def test_forced_window_sizes_both_reduce_modes(M, lib):
+    """every window size 2..20 through the device-pointer entry with both bucket reductions (the bit-plane form splits the
+    2^(c-1) buckets into a 2^ceil((c-1)/2) x 2^floor((c-1)/2) matrix: odd / even c, c = 2 with a single column) -- closed form"""
+    import torch
+    cv = CURVES["bn254_snarks_g1"]
+    n = 3000
+    rng = np.random.default_rng(5)
+    k = rng.integers(1, 2**63, size=n, dtype=np.uint64)
+    pts = _gen_points(lib, cv, k)
+    scal = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    scal[:, 31] &= 0x3F
+    s_int = [int.from_bytes(scal[i].tobytes(), "little") for i in range(n)]
+    want = pyref.ec_mul_fast(sum(s * int(kk) for s, kk in zip(s_int, k)) % cv.fr.modulus, cv.gen, cv)
+    d_s, d_p = torch.from_numpy(scal).cuda(), torch.from_numpy(pts).cuda()
+    try:
+        for mode in (0, 1):
+            lib.ctt_b200_set_reduce_mode(mode)
+            for c in range(2, 21):
+                got = M.msm_device_ptrs(cv, d_s.data_ptr(), d_p.data_ptr(), n, force_c=c)
+                assert pyref.jac_bytes_to_affine(got, cv) == want, (mode, c)
+            # a window range (multi-GPU window sharding): partial sums of two halves add up
+            c, W = M.plan(cv, n)
+            parts = [M.msm_device_ptrs(cv, d_s.data_ptr(), d_p.data_ptr(), n, out=M.OUT_XYZZ, force_c=c, win_begin=a, win_end=b)
+                     for a, b in ((0, W // 2), (W // 2, W))]
+            both = pyref.ec_add(xyzz_bytes_to_affine(parts[0], cv), xyzz_bytes_to_affine(parts[1], cv), cv)
+            assert both == want, mode
+    finally:
+        lib.ctt_b200_set_reduce_mode(0)

@@ -122,3 +122,37 @@ def test_safegcd_model():
     worst = emu.self_test({k: (f.modulus, f.bits) for k, f in FIELDS.items()}, samples=60)
     for name, (used, bound) in worst.items():
         assert used <= bound, name
+
+
+def test_bit_plane_bucket_reduction_identity():
+    """msm_kernels.cuh k_rowcol_sums / k_plane_sums + the host Horner pass of msm_engine.cuh, modelled over the integers
+    (any abelian group): for every window size the c partial "points" P_e reproduce  sum_j (j+1) * bucket[j]."""
+    import random
+    rnd = random.Random(7)
+    for c in range(2, 15):
+        B = 1 << (c - 1)
+        a = (c - 1) // 2
+        rbits = (c - 1) - a
+        C, R = 1 << a, 1 << rbits
+        buckets = [rnd.randrange(-1000, 1000) if rnd.random() < 0.7 else 0 for _ in range(B)]
+        want = sum((j + 1) * b for j, b in enumerate(buckets))
+        H = [sum(buckets[h * C + l] for l in range(C)) for h in range(R)]
+        L = [sum(buckets[h * C + l] for h in range(R)) for l in range(C)]
+        planes = []
+        for p in range(rbits + a + 1):
+            if p < rbits:
+                planes.append((a + p, sum(H[h] for h in range(R) if (h >> p) & 1)))
+            else:
+                b = p - rbits
+                planes.append((b, sum(L[l] for l in range(C) if ((l + 1) >> b) & 1)))
+        assert len(planes) == c
+        assert sum(v << e for e, v in planes) == want, c
+        # the host pass: one doubling per bit position from the top, one addition per non-empty position
+        emax = c - 1
+        by_exp = [0] * (emax + 1)
+        for e, v in planes:
+            by_exp[e] += v
+        r = 0
+        for e in range(emax, -1, -1):
+            r = 2 * r + by_exp[e]
+        assert r == want
