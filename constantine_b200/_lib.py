@@ -90,6 +90,16 @@ def load():
         fn = getattr(lib, nm)
         fn.argtypes = [vp, sz, vp, sz]
         fn.restype = ctypes.c_ubyte
+    lib.ctt_b200_eth_kzg_context_new.argtypes = [vp]
+    lib.ctt_b200_eth_kzg_context_new.restype = vp
+    lib.ctt_b200_eth_kzg_context_new_compressed.argtypes = [vp, ctypes.POINTER(ci)]
+    lib.ctt_b200_eth_kzg_context_new_compressed.restype = vp
+    lib.ctt_b200_eth_kzg_context_precompute.argtypes = [vp, ci]
+    lib.ctt_b200_eth_kzg_context_precompute.restype = ci
+    lib.ctt_b200_eth_kzg_context_delete.argtypes = [vp]
+    lib.ctt_b200_eth_kzg_context_delete.restype = None
+    lib.ctt_b200_eth_kzg_blob_to_kzg_commitment.argtypes = [vp, vp, vp]
+    lib.ctt_b200_eth_kzg_blob_to_kzg_commitment.restype = ctypes.c_ubyte
     lib.ctt_threadpool_new.argtypes = [ci]
     lib.ctt_threadpool_new.restype = vp
     lib.ctt_threadpool_shutdown.argtypes = [vp]

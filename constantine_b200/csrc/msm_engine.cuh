@@ -494,13 +494,18 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
       if (AL >= 2) E.aff_work[0].ensure(level_cap(2) * AFF_BYTES);  // even levels
       E.keys_s.ensure(acc_entries * 4);
       E.vals_s.ensure(acc_entries * 4);
-      // persistent grid of the pair kernel: as many blocks as stay resident
-      int bps = 0;
-      B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_affine_pairs<T, true>, B200_AFF_THREADS, 0));
-      int bps2 = 0;
-      B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps2, k_affine_pairs<T, false>, B200_AFF_THREADS, 0));
-      if (bps2 < bps) bps = bps2;
-      if (bps < 1) bps = 1;
+      // persistent grid of the pair kernel: as many blocks as stay resident (queried once per curve and device: the query
+      // costs tens of microseconds of host time per call, which would stall the launch queue of every MSM)
+      static thread_local int bps_cache[MAX_DEVICES] = {};
+      int bps = bps_cache[E.device];
+      if (bps == 0) {
+        B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_affine_pairs<T, true>, B200_AFF_THREADS, 0));
+        int bps2 = 0;
+        B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps2, k_affine_pairs<T, false>, B200_AFF_THREADS, 0));
+        if (bps2 < bps) bps = bps2;
+        if (bps < 1) bps = 1;
+        bps_cache[E.device] = bps;
+      }
       const unsigned aff_grid = (unsigned)(E.sm_count * bps);
       const size_t aff_threads = (size_t)aff_grid * B200_AFF_THREADS;
       const size_t per_thread = (level_cap(1) + aff_threads - 1) / aff_threads;
@@ -570,7 +575,8 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   // bit-plane reduction (single MSMs): buckets as a 2^rbits x 2^a matrix per window, see k_rowcol_sums
   const bool plane_reduce = (batch == 1 && E.tuning.reduce_mode == 0);
   const int pr_a = (c - 1) / 2, pr_rbits = (c - 1) - pr_a;
-  const uint32_t pr_planes = (uint32_t)c;                       // rbits + a + 1 partial points per window
+  const uint32_t pr_planes = (uint32_t)(c - 1);                 // bit positions 0 .. c-2 of the bucket weights j + 1 = h*C + (l+1) (k_plane_sums)
+  const uint32_t pr_groups = (pr_planes + 3) / 4;               // radix-16 digits per window handed to the host
   uint32_t row = 0;
   DeviceBuffer* src = &E.red_a;
   if (plane_reduce) {
@@ -583,16 +589,19 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
     const int lanes_r = lanes_for(Cn), lanes_c = lanes_for(Rn);
     E.red_a.ensure((size_t)nw * Rn * XYZZ_BYTES);
     E.red_b.ensure((size_t)nw * Cn * XYZZ_BYTES);
-    E.red_planes.ensure((size_t)nw * pr_planes * XYZZ_BYTES);
+    E.red_planes.ensure((size_t)nw * (pr_planes + pr_groups) * XYZZ_BYTES);
     // row sums + column sums of every window, then the bit planes: c partial points per window for the host tail
+    // one launch for both families (the phase is a chain of dependent additions per lane: more warps in flight hide it better)
     const size_t tr = (size_t)nw * Rn * lanes_r, tc = (size_t)nw * Cn * lanes_c;
-    k_rowcol_sums<T, INL, false><<<(unsigned)((tr + 127) / 128), 128, 0, s>>>((const uint32_t*)E.buckets.ptr, B, pr_a, (uint32_t)nw, lanes_r,
-                                                                              (uint32_t*)E.red_a.ptr);
-    k_rowcol_sums<T, INL, true><<<(unsigned)((tc + 127) / 128), 128, 0, s>>>((const uint32_t*)E.buckets.ptr, B, pr_a, (uint32_t)nw, lanes_c,
-                                                                             (uint32_t*)E.red_b.ptr);
+    const unsigned row_blocks = (unsigned)((tr + 127) / 128), col_blocks = (unsigned)((tc + 127) / 128);
+    k_rowcol_sums<T, INL><<<row_blocks + col_blocks, 128, 0, s>>>((const uint32_t*)E.buckets.ptr, B, pr_a, (uint32_t)nw, lanes_r, lanes_c, row_blocks,
+                                                                  (uint32_t*)E.red_a.ptr, (uint32_t*)E.red_b.ptr);
     const size_t tp = (size_t)nw * pr_planes * 32;
+    uint32_t* planes_ptr = (uint32_t*)E.red_planes.ptr;
+    uint32_t* digits_ptr = planes_ptr + (size_t)nw * pr_planes * XW;
     k_plane_sums<T, INL><<<(unsigned)((tp + 127) / 128), 128, 0, s>>>((const uint32_t*)E.red_a.ptr, (const uint32_t*)E.red_b.ptr, pr_a, pr_rbits,
-                                                                      (uint32_t)nw, (uint32_t*)E.red_planes.ptr);
+                                                                      (uint32_t)nw, planes_ptr);
+    k_plane_combine<T, INL><<<(unsigned)(((size_t)nw * pr_groups + 63) / 64), 64, 0, s>>>(planes_ptr, pr_planes, pr_groups, (uint32_t)nw, digits_ptr);
     launches += 3;
   } else {
     // running-sum chunks, offsets, warp-butterfly row sums (<= 4 per window left; batches: one)
@@ -660,22 +669,22 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   // ec_multi_scalar_mul_parallel.nim:198-203: c doublings + one addition per window), including the shift by c*win_begin.
   HP r = HP::inf();
   if (plane_reduce) {
-    // window w arrives as c partial points with S_w = sum_p 2^e(p) P_p: e = a + p for the row planes, p - rbits for the column
-    // planes; one doubling per bit position, one addition per non-empty position
-    const size_t out_bytes = (size_t)nw * pr_planes * XYZZ_BYTES;
+    // window w arrives as radix-16 digits D_g of its sum, S_w = sum_g 16^g D_g: one doubling per bit position, one addition
+    // per digit
+    const size_t out_bytes = (size_t)nw * pr_groups * XYZZ_BYTES;
     E.ensure_host(out_bytes);
-    B200_CUDA_CHECK(cudaMemcpyAsync(E.h_result, E.red_planes.ptr, out_bytes, cudaMemcpyDeviceToHost, s));
+    B200_CUDA_CHECK(cudaMemcpyAsync(E.h_result, (const uint32_t*)E.red_planes.ptr + (size_t)nw * pr_planes * XW, out_bytes, cudaMemcpyDeviceToHost, s));
     B200_CUDA_CHECK(cudaStreamSynchronize(s));
     const HP* parts = reinterpret_cast<const HP*>(E.h_result);
     const int wshift = table_mode ? 0 : plan.win_begin;
-    const int emax = c * (wshift + nw - 1) + (c - 1);
+    const int emax = c * (wshift + nw - 1) + 4 * ((int)pr_groups - 1);
     static thread_local std::vector<HP> by_exp;
     by_exp.assign((size_t)emax + 1, HP::inf());
     for (int w = 0; w < nw; w++)
-      for (uint32_t p = 0; p < pr_planes; p++) {
-        const HP& pt = parts[(size_t)w * pr_planes + p];
+      for (uint32_t g = 0; g < pr_groups; g++) {
+        const HP& pt = parts[(size_t)w * pr_groups + g];
         if (pt.is_inf()) continue;
-        const int e = c * (wshift + w) + ((int)p < pr_rbits ? pr_a + (int)p : (int)p - pr_rbits);
+        const int e = c * (wshift + w) + 4 * (int)g;
         by_exp[e] = host::xyzz_add(by_exp[e], pt);
       }
     for (int e = emax; e >= 0; e--) {
@@ -734,11 +743,14 @@ host::HXyzz<typename C::H> msm_host_on(int device, const void* coefs, const void
   E.d_points.ensure(pbytes);
   cudaEvent_t t0 = E.ev[7], t1 = E.ev[8];
   B200_CUDA_CHECK(cudaEventRecord(t0, E.compute()));
-  // Large inputs cross PCIe in a few chunks (scalars and points of chunk k, then chunk k+1, all on the copy stream) and the
-  // engine starts on chunk k as soon as it has landed: only the first chunk's transfer is exposed. Small inputs go in one
-  // piece: scalars on the compute stream (digits + sort need only them), points on the copy stream beside them.
+  // One piece (default): scalars on the compute stream (digits + sort need only them), points on the copy stream beside them.
+  // Chunked (ctt_b200_set_input_chunks): scalars and points of chunk k, then chunk k+1, all on the copy stream; the engine
+  // starts on chunk k as soon as it has landed and accumulates every chunk into the same buckets.
+  // Measured at N = 2^20 (profiles/README.md, round 2): every extra chunk costs more (shorter runs per chunk: fewer batched-affine
+  // levels, one more plan / fix-up pass) than the transfer it hides -- 9.9 / 10.2 / 10.4 / 11.0 ms for 1 / 2 / 3 / 4 chunks -- so
+  // the default is one piece; the knob stays for links slower than this box's PCIe 5 x16.
   int P = E.tuning.input_chunks;
-  if (P <= 0) P = len >= (1u << 19) ? 4 : (len >= (1u << 17) ? 2 : 1);
+  if (P <= 0) P = 1;
   if (P > Engine::MAX_INPUT_CHUNKS) P = Engine::MAX_INPUT_CHUNKS;
   HP r;
   if (P > 1) {

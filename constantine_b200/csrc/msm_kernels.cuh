@@ -363,8 +363,9 @@ __global__ void __launch_bounds__(128) k_row_sum_warp(const uint32_t* in, uint32
 //   j + 1 = h*C + (l + 1)  and   S = C * sum_h h*H_h + sum_l (l+1)*L_l   with the row sums H_h and the column sums L_l;
 //   a sum  sum_i i*X_i  over 2^k points is  sum_b 2^b * (sum of the X_i whose index has bit b set): "bit planes".
 //   k_rowcol_sums: every row sum and every column sum, `lanes` lanes per sum (strided serial part + xor butterfly);
-//   k_plane_sums : one warp per (window, plane): rbits planes of H (bits of h), a+1 planes of L (bits of l+1).
-// A window leaves the device as c partial points P_e with  S = sum_e 2^e P_e; the host tail folds the 2^e into the
+//   k_plane_sums : one warp per (window, bit position q of the weight j+1), q = 0 .. c-2;
+//   k_plane_combine: radix-16 digits D_g = sum_{k<4} 2^k P_{4g+k} of the c-1 bit-position sums.
+// A window leaves the device as ceil((c-1)/4) partial points with  S = sum_g 16^g D_g; the host tail folds the 16^g into the
 // Horner evaluation over the windows it runs anyway (one doubling per bit position, one addition per partial point).
 // Work: 2 additions per bucket as before, but the longest dependent chain is C/lanes + R/lanes + 2 log2(lanes) + ~13
 // additions instead of ~66, and every stage is a plain sum (any number of lanes per sum).
@@ -384,15 +385,17 @@ B200_DEV void group_butterfly(Xyzz<T>& acc, int lanes) {
   }
 }
 
-// COLS = false: out[w*R + h] = sum_l bucket[w][h*C + l];  COLS = true: out[w*C + l] = sum_h bucket[w][h*C + l].
-// `lanes` (power of two <= 32) lanes share one sum; the grid is a whole number of warps and every lane reaches the shuffles.
-template <class T, bool INL, bool COLS>
+// Blocks [0, row_blocks): out_rows[w*R + h] = sum_l bucket[w][h*C + l];  the others: out_cols[w*C + l] = sum_h bucket[w][h*C + l].
+// `lanes` (power of two <= 32) lanes share one sum; a block is a whole number of warps and every lane reaches the shuffles.
+template <class T, bool INL>
 __global__ void __launch_bounds__(128) k_rowcol_sums(const uint32_t* buckets, uint32_t buckets_per_window, int a, uint32_t num_windows,
-                                                     int lanes, uint32_t* out) {
+                                                     int lanes_r, int lanes_c, unsigned row_blocks, uint32_t* out_rows, uint32_t* out_cols) {
+  const bool cols = blockIdx.x >= row_blocks;               // uniform per block
   const uint32_t C = 1u << a, R = buckets_per_window >> a;
-  const uint32_t per_window = COLS ? C : R;                 // sums per window
-  const uint32_t len = COLS ? R : C;                        // terms per sum
-  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t per_window = cols ? C : R;                 // sums per window
+  const uint32_t len = cols ? R : C;                        // terms per sum
+  const int lanes = cols ? lanes_c : lanes_r;
+  const size_t g = (size_t)(blockIdx.x - (cols ? row_blocks : 0u)) * blockDim.x + threadIdx.x;
   const size_t sum_id = g / (unsigned)lanes;
   const uint32_t t = (uint32_t)(g % (unsigned)lanes);
   const bool live = sum_id < (size_t)per_window * num_windows;
@@ -400,31 +403,35 @@ __global__ void __launch_bounds__(128) k_rowcol_sums(const uint32_t* buckets, ui
   if (live) {
     const uint32_t w = (uint32_t)(sum_id / per_window), i = (uint32_t)(sum_id % per_window);
     const size_t base = (size_t)w * buckets_per_window;
+    // row sum: elements i*C + k (stride 1);  column sum: elements k*C + i (stride C)
+    const size_t first = cols ? (size_t)i : (size_t)i * C;
+    const size_t stride = cols ? (size_t)C : 1;
 #pragma unroll 1
     for (uint32_t k = t; k < len; k += (uint32_t)lanes) {
-      const size_t j = COLS ? ((size_t)k * C + i) : ((size_t)i * C + k);
-      Xyzz<T> b = load_xyzz<T>(buckets, base + j);
+      Xyzz<T> b = load_xyzz<T>(buckets, base + first + (size_t)k * stride);
       padd<T, INL>(acc, b);
     }
   }
   group_butterfly<T, INL>(acc, lanes);
-  if (live && t == 0) store_xyzz(out, sum_id, acc);
+  if (live && t == 0) store_xyzz(cols ? out_cols : out_rows, sum_id, acc);
 }
 
-// One warp per (window w, plane p): p < rbits: H plane (bit p of the row index h); p >= rbits: L plane b = p - rbits
-// (bit b of l + 1).  out[w * (rbits + a + 1) + p].
+// One warp per (window w, bit position q), q = 0 .. c-2:  P_q = sum of everything that carries weight bit q of j + 1 = h*C + (l+1):
+//   q <  a: the column sums L_l with bit q of l + 1 set (l + 1 = C has no bit below a);
+//   q >= a: the row sums H_h with bit q - a of h set, and for q == a also the last column L_{C-1} (its weight l + 1 = C = 2^a).
+// Then S_w = sum_q 2^q P_q.  out[w * (c - 1) + q].
 template <class T, bool INL>
 __global__ void __launch_bounds__(128) k_plane_sums(const uint32_t* row_sums, const uint32_t* col_sums, int a, int rbits,
                                                     uint32_t num_windows, uint32_t* out) {
   const unsigned lane = threadIdx.x & 31u;
   const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t planes = (uint32_t)(rbits + a + 1);
+  const uint32_t planes = (uint32_t)(rbits + a);
   const bool live = warp < (size_t)planes * num_windows;
   Xyzz<T> acc = Xyzz<T>::inf();
   if (live) {
-    const uint32_t w = (uint32_t)(warp / planes), p = (uint32_t)(warp % planes);
-    const bool is_h = p < (uint32_t)rbits;
-    const uint32_t bit = is_h ? p : p - (uint32_t)rbits;
+    const uint32_t w = (uint32_t)(warp / planes), q = (uint32_t)(warp % planes);
+    const bool is_h = q >= (uint32_t)a;
+    const uint32_t bit = is_h ? q - (uint32_t)a : q;
     const uint32_t len = is_h ? (1u << rbits) : (1u << a);
     const uint32_t* src = is_h ? row_sums : col_sums;
     const size_t base = (size_t)w * len;
@@ -436,9 +443,34 @@ __global__ void __launch_bounds__(128) k_plane_sums(const uint32_t* row_sums, co
         padd<T, INL>(acc, b);
       }
     }
+    if (q == (uint32_t)a && lane == 0) {
+      Xyzz<T> b = load_xyzz<T>(col_sums, (size_t)w * (1u << a) + ((1u << a) - 1u));
+      padd<T, INL>(acc, b);
+    }
   }
   group_butterfly<T, INL>(acc, 32);
   if (live && lane == 0) store_xyzz(out, warp, acc);
+}
+
+// Radix-16 digits of the window sums: out[w * groups + g] = sum_{k<4} 2^k P_{4g+k} (three doublings and up to three additions per
+// thread), so that the host tail adds one point per FOUR bit positions instead of one per position.
+template <class T, bool INL>
+__global__ void __launch_bounds__(64) k_plane_combine(const uint32_t* planes_in, uint32_t planes, uint32_t groups, uint32_t num_windows,
+                                                      uint32_t* out) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (size_t)groups * num_windows) return;
+  const uint32_t w = (uint32_t)(g / groups), grp = (uint32_t)(g % groups);
+  Xyzz<T> r = Xyzz<T>::inf();
+#pragma unroll 1
+  for (int k = 3; k >= 0; k--) {
+    pdbl<T, INL>(r);
+    const uint32_t q = 4u * grp + (uint32_t)k;
+    if (q < planes) {
+      Xyzz<T> b = load_xyzz<T>(planes_in, (size_t)w * planes + q);
+      padd<T, INL>(r, b);
+    }
+  }
+  store_xyzz(out, g, r);
 }
 
 // Batch tail: one thread per MSM of a batch. parts[(m * nwd + w) * row + i] are the <= 4 partial sums of window w of

@@ -266,3 +266,39 @@ def eth_evm_bls12381_g2msm(inputs: bytes, out_len: int = 256):
     r = ctypes.create_string_buffer(out_len)
     st = _lib.load().ctt_eth_evm_bls12381_g2msm(r, out_len, bytes(inputs), len(inputs))
     return EVM_STATUS[st], r.raw
+
+
+class EthKzgContext:
+    """EIP-4844 commitment context on the resident SRS, the role of the reference's EthereumKZGContext for
+    blob_to_kzg_commitment[_parallel] (reference constantine/ethereum_eip4844_kzg_parallel.nim:125-159)."""
+
+    ScalarLargerThanCurveOrder = 4        # cttEthKzg_ScalarLargerThanCurveOrder
+
+    def __init__(self, srs_lagrange_brp_g1, compressed=True):
+        lib = _lib.load()
+        buf = _buf(srs_lagrange_brp_g1)
+        if compressed:
+            st = ctypes.c_int(0)
+            self._h = lib.ctt_b200_eth_kzg_context_new_compressed(buf, ctypes.byref(st))
+            if not self._h:
+                raise ValueError(f"trusted setup point does not decode (cttEthKzg status {st.value})")
+        else:
+            self._h = lib.ctt_b200_eth_kzg_context_new(buf)
+            if not self._h:
+                raise ValueError("ctt_b200_eth_kzg_context_new failed")
+
+    def precompute(self, c: int = 0) -> int:
+        return _lib.load().ctt_b200_eth_kzg_context_precompute(self._h, c)
+
+    def blob_to_kzg_commitment(self, blob) -> bytes:
+        """48-byte compressed commitment; raises ValueError carrying the reference's status code for an invalid blob."""
+        dst = ctypes.create_string_buffer(48)
+        rc = _lib.load().ctt_b200_eth_kzg_blob_to_kzg_commitment(self._h, dst, _buf(blob))
+        if rc != 0:
+            raise ValueError(rc)
+        return dst.raw
+
+    def delete(self):
+        if self._h:
+            _lib.load().ctt_b200_eth_kzg_context_delete(self._h)
+            self._h = None

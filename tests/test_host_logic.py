@@ -125,8 +125,8 @@ def test_safegcd_model():
 
 
 def test_bit_plane_bucket_reduction_identity():
-    """msm_kernels.cuh k_rowcol_sums / k_plane_sums + the host Horner pass of msm_engine.cuh, modelled over the integers
-    (any abelian group): for every window size the c partial "points" P_e reproduce  sum_j (j+1) * bucket[j]."""
+    """msm_kernels.cuh k_rowcol_sums / k_plane_sums / k_plane_combine + the host Horner pass of msm_engine.cuh, modelled over the
+    integers (any abelian group): for every window size the radix-16 digits reproduce  sum_j (j+1) * bucket[j]."""
     import random
     rnd = random.Random(7)
     for c in range(2, 15):
@@ -139,19 +139,27 @@ def test_bit_plane_bucket_reduction_identity():
         H = [sum(buckets[h * C + l] for l in range(C)) for h in range(R)]
         L = [sum(buckets[h * C + l] for h in range(R)) for l in range(C)]
         planes = []
-        for p in range(rbits + a + 1):
-            if p < rbits:
-                planes.append((a + p, sum(H[h] for h in range(R) if (h >> p) & 1)))
+        for q in range(c - 1):
+            if q < a:
+                planes.append(sum(L[l] for l in range(C) if ((l + 1) >> q) & 1))
             else:
-                b = p - rbits
-                planes.append((b, sum(L[l] for l in range(C) if ((l + 1) >> b) & 1)))
-        assert len(planes) == c
-        assert sum(v << e for e, v in planes) == want, c
-        # the host pass: one doubling per bit position from the top, one addition per non-empty position
-        emax = c - 1
+                v = sum(H[h] for h in range(R) if (h >> (q - a)) & 1)
+                if q == a:
+                    v += L[C - 1]
+                planes.append(v)
+        assert sum(v << q for q, v in enumerate(planes)) == want, c
+        groups = (len(planes) + 3) // 4
+        digits = []
+        for g in range(groups):
+            r = 0
+            for k in (3, 2, 1, 0):
+                r = 2 * r + (planes[4 * g + k] if 4 * g + k < len(planes) else 0)
+            digits.append(r)
+        # the host pass: one doubling per bit position from the top, one addition per digit
+        emax = 4 * (groups - 1)
         by_exp = [0] * (emax + 1)
-        for e, v in planes:
-            by_exp[e] += v
+        for g, v in enumerate(digits):
+            by_exp[4 * g] += v
         r = 0
         for e in range(emax, -1, -1):
             r = 2 * r + by_exp[e]

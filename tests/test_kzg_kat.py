@@ -45,3 +45,28 @@ def test_cuda_path_reproduces_kzg_commitments(kzg):
         got = pyref.prj_bytes_to_affine(M.multi_scalar_mul_vartime_parallel(tp, cv, cbm, pb, 4096, out="prj", coef_kind="fr"), cv)
         assert pyref.bls12_381_g1_compress(got, cv) == want
     tp.shutdown()
+
+
+@pytest.mark.gpu
+def test_blob_to_kzg_commitment_entry(kzg):
+    """The reference's blob_to_kzg_commitment vectors byte for byte through the commitment entry on the resident SRS
+    (ctt_b200_eth_kzg_*): blob bytes in, 48-byte compressed commitment out; context from the compressed trusted-setup points
+    and from affine Montgomery structs, with and without the precomputed window table; a blob element >= r is refused with
+    the reference's status (reference tests: blob_to_kzg_commitment/kzg-mainnet/*invalid_blob*)."""
+    from constantine_b200 import msm as M
+    cv, pb, cases = kzg
+    z = np.load(os.path.join(ROOT, "tests", "golden", "kzg_commit_kat.npz"))
+    for ctx in (M.EthKzgContext(z["srs_lagrange_brp_compressed"].tobytes(), compressed=True), M.EthKzgContext(pb, compressed=False)):
+        for table in (False, True):
+            if table:
+                assert ctx.precompute(0) >= 2
+            for blob, want in zip(z["blobs"], z["commitments"]):
+                assert ctx.blob_to_kzg_commitment(blob.tobytes()) == bytes(want)
+        bad = bytearray(z["blobs"][0].tobytes())
+        bad[32 * 5:32 * 6] = cv.fr.modulus.to_bytes(32, "big")
+        with pytest.raises(ValueError) as e:
+            ctx.blob_to_kzg_commitment(bytes(bad))
+        assert e.value.args[0] == M.EthKzgContext.ScalarLargerThanCurveOrder
+        zero = bytes(4096 * 32)                              # the zero polynomial commits to the point at infinity
+        assert ctx.blob_to_kzg_commitment(zero) == bytes([0xC0]) + bytes(47)
+        ctx.delete()

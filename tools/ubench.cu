@@ -122,6 +122,23 @@ __global__ void __launch_bounds__(128) k_madd_chain(const uint32_t* pts, uint32_
   store_xyzz(out, (size_t)i, acc);
 }
 
+// two-pipe multiplier variants (field.cuh fe_mul_v): MASK selects which product rows go through IMAD.WIDE (no addend) + ALU adds
+template <class F, int MASK>
+__global__ void __launch_bounds__(128) k_mul_chain_v(const uint32_t* in, uint32_t* out, int n, int iters) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  typedef Fp<F> T;
+  T x, y;
+  load_words(x, in + (size_t)(2 * i) * T::WORDS);
+  load_words(y, in + (size_t)(2 * i + 1) * T::WORDS);
+#pragma unroll 1
+  for (int k = 0; k < iters; k++) {
+    if constexpr (MASK < 0) { fe_mul<F>(x.l, x.l, y.l); fe_mul<F>(y.l, y.l, x.l); }
+    else { fe_mul_v<F, MASK>(x.l, x.l, y.l); fe_mul_v<F, MASK>(y.l, y.l, x.l); }
+  }
+  store_words(out + (size_t)i * T::WORDS, x + y);
+}
+
 static uint64_t rng_state = 0x9E3779B97F4A7C15ull;
 static uint64_t rnd64() { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17; return rng_state; }
 
@@ -171,6 +188,65 @@ void bench_field(const char* name, int sms, double clock_ghz) {
          "\"int_macs_per_mul\":%d,\"Tmac_per_s\":%.2f}\n",
          name, bad, ms, per_s * 1e-9, sms * clock_ghz * 1e9 / per_s, 2 * L * L + L, per_s * (2 * L * L + L) * 1e-12);
   cudaFree(d_in); cudaFree(d_out);
+}
+
+template <class F, int MASK>
+void bench_field_v(const char* name, int sms, double clock_ghz) {
+  typedef Fp<F> T;
+  typedef host::HFp<F> H;
+  const int n = sms * 2048, iters = 64;
+  std::vector<H> in(2 * n);
+  for (auto& v : in) v = rand_fe<F>();
+  uint32_t *d_in, *d_out;
+  CK(cudaMalloc(&d_in, sizeof(H) * 2 * n));
+  CK(cudaMalloc(&d_out, sizeof(H) * n));
+  CK(cudaMemcpy(d_in, in.data(), sizeof(H) * 2 * n, cudaMemcpyHostToDevice));
+  int threads = 128;
+  k_mul_chain_v<F, MASK><<<(n + threads - 1) / threads, threads>>>(d_in, d_out, n, 2);
+  CK(cudaDeviceSynchronize());
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0);
+    k_mul_chain_v<F, MASK><<<(n + threads - 1) / threads, threads>>>(d_in, d_out, n, iters);
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  std::vector<H> out(n);
+  CK(cudaMemcpy(out.data(), d_out, sizeof(H) * n, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  for (int i = 0; i < 512; i++) {
+    H x = in[2 * i], y = in[2 * i + 1];
+    for (int k = 0; k < iters; k++) { x = x * y; y = y * x; }
+    H r = x + y;
+    if (!(r == out[i])) bad++;
+  }
+  int regs = 0;
+  { cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k_mul_chain_v<F, MASK>); regs = fa.numRegs; }
+  double muls = (double)n * iters * 2;
+  double per_s = muls / (best * 1e-3);
+  int L = F::N;
+  printf("{\"bench\":\"fe_mul_two_pipe\",\"field\":\"%s\",\"alu_row_mask\":%d,\"regs\":%d,\"mismatch_of_512\":%d,\"ms\":%.4f,\"Gmul_per_s\":%.2f,"
+         "\"clk_per_mul_per_sm\":%.2f,\"Tmac_per_s\":%.2f}\n",
+         name, MASK, regs, bad, best, per_s * 1e-9, sms * clock_ghz * 1e9 / per_s, per_s * (2 * L * L + L) * 1e-12);
+  fflush(stdout);
+  cudaFree(d_in); cudaFree(d_out);
+}
+
+template <class F>
+void bench_two_pipe(const char* name, int sms, double clock_ghz) {
+  bench_field_v<F, -1>(name, sms, clock_ghz);   // fe_mul as shipped (all rows on the multiplier pipe)
+  bench_field_v<F, 0>(name, sms, clock_ghz);
+  bench_field_v<F, 1>(name, sms, clock_ghz);
+  bench_field_v<F, 4>(name, sms, clock_ghz);
+  bench_field_v<F, 5>(name, sms, clock_ghz);
+  bench_field_v<F, 10>(name, sms, clock_ghz);
+  bench_field_v<F, 3>(name, sms, clock_ghz);
+  bench_field_v<F, 12>(name, sms, clock_ghz);
+  bench_field_v<F, 7>(name, sms, clock_ghz);
+  bench_field_v<F, 15>(name, sms, clock_ghz);
 }
 
 // ---------------------------------------------------------------- reduced-radix (carry-free) multiplier prototype
@@ -334,6 +410,9 @@ int main() {
   run_pipe<5>("add.cc chain", sms, clock_ghz);
   run_pipe<6>("mad.lo.u32 + fma.f64 interleaved", sms, clock_ghz);
   run_pipe<7>("mad.lo.u32 + add.u32 interleaved", sms, clock_ghz);
+  bench_two_pipe<Bls12381Fp>("bls12_381_fp", sms, clock_ghz);
+  bench_two_pipe<Bn254SnarksFp>("bn254_snarks_fp", sms, clock_ghz);
+  if (getenv("UBENCH_TWO_PIPE_ONLY")) return 0;
   bench_field<Bls12381Fp>("bls12_381_fp", sms, clock_ghz);
   bench_field<Bn254SnarksFp>("bn254_snarks_fp", sms, clock_ghz);
   bench_field<PallasFp>("pallas_fp", sms, clock_ghz);
