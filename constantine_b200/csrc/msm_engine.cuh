@@ -159,6 +159,17 @@ struct Engine {
   DeviceBuffer aff_head, aff_tail, aff_off, aff_blocksum, aff_plan[AFF_MAX_LEVELS], aff_work[2], aff_scratch, keys_s, vals_s;
   void* h_result = nullptr;   // pinned
   size_t h_result_cap = 0;
+  // pinned double buffer through which pageable caller memory is staged (msm_host_on)
+  static constexpr size_t STAGE_BYTES = 16u << 20;
+  void* h_stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+  void ensure_stage() {
+    if (h_stage[0]) return;
+    for (int i = 0; i < 2; i++) {
+      B200_CUDA_CHECK(cudaMallocHost(&h_stage[i], STAGE_BYTES));
+      B200_CUDA_CHECK(cudaEventCreateWithFlags(&ev_stage[i], cudaEventDisableTiming));
+    }
+  }
   void ensure_host(size_t bytes) {
     if (bytes <= h_result_cap) return;
     if (h_result) B200_CUDA_CHECK(cudaFreeHost(h_result));
@@ -478,8 +489,10 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
     const size_t max_fix = (max_slices + KFIX - 1) / KFIX;
     E.part_pts[0].ensure(max_slices * XYZZ_BYTES); E.part_keys[0].ensure(max_slices * 4);
     E.part_pts[1].ensure(max_fix * XYZZ_BYTES); E.part_keys[1].ensure(max_fix * 4);
-    // points of a chunked / host call arrive on the copy stream
-    if (!input_chunks && ch.ready) B200_CUDA_CHECK(cudaStreamWaitEvent(s, ch.ready, 0));
+    // points of a host call arrive on the copy stream: nothing up to here reads them, and neither does the batched-affine plan
+    // below (run bounds, level offsets, pair lists come from the sorted keys / refs alone), so the wait sits right in front of
+    // the first kernel that gathers points
+    auto wait_for_points = [&]() { if (!input_chunks && ch.ready) B200_CUDA_CHECK(cudaStreamWaitEvent(s, ch.ready, 0)); };
     const void* acc_points = pts;
     if (AL) {
       const uint32_t nb = (uint32_t)nbuckets;
@@ -527,6 +540,7 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
       aplan.surv_keys = (uint32_t*)E.keys_s.ptr;
       aplan.surv_vals = (uint32_t*)E.vals_s.ptr;
       k_affine_plan<<<eb, 256, 0, s>>>(keys, vals, entries, no_key, head, tail, off, nb, AL, aplan);
+      wait_for_points();
       for (int r = 0; r < AL; r++) {
         const uint32_t* total_ptr = off + (size_t)(r + 1) * off_stride + nb;      // size of level r + 1
         uint32_t* dst = (uint32_t*)E.aff_work[(r + 1) & 1].ptr;
@@ -544,6 +558,7 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
       if (timed) B200_CUDA_CHECK(cudaEventRecord(E.ev[9], s));
     }
     st.affine_levels = AL;
+    if (!AL) wait_for_points();
     // 3. accumulate
     {
       dim3 block(B200_ACC_THREADS), grid((unsigned)((max_slices + B200_ACC_THREADS - 1) / B200_ACC_THREADS));
@@ -731,6 +746,97 @@ void write_result(void* r_out, const host::HXyzz<typename C::H>& p, int kind) {
   memcpy(o + 2 * sizeof(H), &Z, sizeof(H));
 }
 
+// ---- pageable caller memory --------------------------------------------------------------------------------------
+// The reference's callers pass ordinary heap memory. cudaMemcpyAsync from pageable memory goes through the driver's small
+// bounce buffer at a fraction of the PCIe rate (measured: the 128 MiB of an N = 2^20 MSM take ~12 ms instead of ~3 ms), so
+// such inputs are staged here instead: a few persistent host threads copy 16 MiB pieces into a pinned double buffer while the
+// DMA engine moves the previous piece.
+struct HostCopyPool {
+  struct Slot {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    char* dst = nullptr; const char* src = nullptr; size_t bytes = 0;
+    bool has_job = false, done = true;
+  };
+  std::mutex mu;                       // one staged copy at a time uses the helpers
+  std::vector<Slot*> slots;
+  int threads = 0;
+  void ensure() {
+    if (threads) return;
+    int t = 6;
+    if (const char* v = getenv("CTT_B200_STAGE_THREADS")) t = atoi(v);
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && t > hw) t = hw;
+    if (t < 1) t = 1;
+    threads = t;
+    for (int i = 0; i + 1 < t; i++) {
+      Slot* sl = new Slot;
+      sl->th = std::thread([sl] {
+        for (;;) {
+          std::unique_lock<std::mutex> lk(sl->m);
+          sl->cv.wait(lk, [&] { return sl->has_job; });
+          sl->has_job = false;
+          lk.unlock();
+          memcpy(sl->dst, sl->src, sl->bytes);
+          lk.lock();
+          sl->done = true;
+          lk.unlock();
+          sl->cv.notify_all();
+        }
+      });
+      sl->th.detach();
+      slots.push_back(sl);
+    }
+  }
+  // dst <- src, split evenly over the helpers and the calling thread
+  void copy(void* dst, const void* src, size_t bytes) {
+    const size_t parts = (size_t)threads;
+    if (parts <= 1 || bytes < (1u << 20)) { memcpy(dst, src, bytes); return; }
+    const size_t per = ((bytes / parts) + 4095) & ~(size_t)4095;
+    size_t off = 0;
+    size_t used = 0;
+    for (; used < slots.size() && off + per < bytes; used++, off += per) {
+      Slot* sl = slots[used];
+      { std::lock_guard<std::mutex> lk(sl->m); sl->dst = (char*)dst + off; sl->src = (const char*)src + off; sl->bytes = per; sl->has_job = true; sl->done = false; }
+      sl->cv.notify_all();
+    }
+    memcpy((char*)dst + off, (const char*)src + off, bytes - off);
+    for (size_t i = 0; i < used; i++) {
+      Slot* sl = slots[i];
+      std::unique_lock<std::mutex> lk(sl->m);
+      sl->cv.wait(lk, [&] { return sl->done; });
+    }
+  }
+};
+inline HostCopyPool& host_copy_pool() {
+  static HostCopyPool* p = new HostCopyPool;   // leaked with the process (detached threads)
+  return *p;
+}
+
+inline bool is_pageable_host_memory(const void* p) {
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return true; }
+  return at.type == cudaMemoryTypeUnregistered;
+}
+
+// device <- pageable host memory through the engine's pinned double buffer, on `st`
+inline void staged_h2d(Engine& E, void* d_dst, const void* h_src, size_t bytes, cudaStream_t st, int& piece) {
+  HostCopyPool& pool = host_copy_pool();
+  size_t off = 0;
+  while (off < bytes) {
+    const size_t n = bytes - off < Engine::STAGE_BYTES ? bytes - off : Engine::STAGE_BYTES;
+    const int buf = piece & 1;
+    if (piece >= 2) B200_CUDA_CHECK(cudaEventSynchronize(E.ev_stage[buf]));   // the DMA that last read this buffer is done
+    pool.copy(E.h_stage[buf], (const char*)h_src + off, n);
+    B200_CUDA_CHECK(cudaMemcpyAsync((char*)d_dst + off, E.h_stage[buf], n, cudaMemcpyHostToDevice, st));
+    B200_CUDA_CHECK(cudaEventRecord(E.ev_stage[buf], st));
+    off += n;
+    piece++;
+  }
+}
+
 // ---- host-pointer entry (the reference's C ABI semantics): copy in, run, convert ----------------------------------
 // One device: copy `len` pairs in, run the engine, return the raw XYZZ result.
 template <class C>
@@ -765,6 +871,19 @@ host::HXyzz<typename C::H> msm_host_on(int device, const void* coefs, const void
     }
     B200_CUDA_CHECK(cudaEventRecord(t1, E.compute()));
     r = msm_device<C>(E, E.d_scalars.ptr, E.d_points.ptr, len, fr_mont, 0, 0, -1, nullptr, 0, 1, false, nullptr, &chunks);
+  } else if (sbytes + pbytes >= (8u << 20) && (is_pageable_host_memory(coefs) || is_pageable_host_memory(points))) {
+    // pageable caller memory: stage it (scalars first, then the points) through the pinned double buffer
+    HostCopyPool& pool = host_copy_pool();
+    std::lock_guard<std::mutex> lk(pool.mu);
+    pool.ensure();
+    E.ensure_stage();
+    int piece = 0;
+    staged_h2d(E, E.d_scalars.ptr, coefs, sbytes, E.copy_stream, piece);
+    staged_h2d(E, E.d_points.ptr, points, pbytes, E.copy_stream, piece);
+    B200_CUDA_CHECK(cudaEventRecord(E.ev_points_ready, E.copy_stream));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(E.compute(), E.ev_points_ready, 0));
+    B200_CUDA_CHECK(cudaEventRecord(t1, E.compute()));
+    r = msm_device<C>(E, E.d_scalars.ptr, E.d_points.ptr, len, fr_mont, 0, 0, -1, nullptr);
   } else {
     B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, sbytes, cudaMemcpyHostToDevice, E.compute()));
     B200_CUDA_CHECK(cudaMemcpyAsync(E.d_points.ptr, points, pbytes, cudaMemcpyHostToDevice, E.copy_stream));

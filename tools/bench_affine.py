@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--logn", type=int, default=20)
     ap.add_argument("--levels", default="0,1,2,3,4")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--cs", default="0", help="forced window sizes to sweep (0 = the engine's choice)")
     a = ap.parse_args()
     import torch
     from constantine_b200 import _lib, msm as M
@@ -36,12 +37,12 @@ def main():
     want = pyref.ec_mul_fast(e, cv.gen, cv)
     d_pts = torch.from_numpy(pts).cuda()
     d_s = torch.from_numpy(s).cuda()
-    for lv in [int(x) for x in a.levels.split(",")]:
+    for lv, fc in [(int(x), int(y)) for y in a.cs.split(",") for x in a.levels.split(",")]:
         lib.ctt_b200_set_affine_levels(lv)
         ok = True
         best = None
         for _ in range(a.reps):
-            got = M.msm_device_ptrs(cv, d_s.data_ptr(), d_pts.data_ptr(), n)
+            got = M.msm_device_ptrs(cv, d_s.data_ptr(), d_pts.data_ptr(), n, force_c=fc)
             ok = ok and pyref.jac_bytes_to_affine(got, cv) == want
             st = M.last_stats()
             if best is None or st["ms_total"] < best["ms_total"]:
