@@ -289,8 +289,7 @@ def main():
     def step_resident():
         if world == 1:
             return M.msm_device_ptrs(cv, d_scal.data_ptr(), d_pts.data_ptr(), n, out=M.OUT_JAC)
-        part = M.msm_device_ptrs(cv, d_scal.data_ptr(), d_pts.data_ptr(), n, out=M.OUT_XYZZ, force_c=c_plan, win_begin=wb, win_end=we)
-        return sharded.msm_point_sharded(cv, part, device=dev)
+        return sharded.msm_window_sharded_device(cv, d_scal.data_ptr(), d_pts.data_ptr(), n, c_plan, W_plan, device=dev)
 
     symbol = f"ctt_{cv.cprefix}_jac_multi_scalar_mul_big_coefs_vartime_parallel"
     named = _lib.named_msm(symbol)
@@ -420,8 +419,8 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload_string(CURVE, args.logn),
-                   "parallelism": "1 GPU" if world == 1 else (f"resident leg: inputs replicated, {W_plan} windows sharded over {world} GPUs; "
-                                                                  f"e2e leg: points sharded over {world} GPUs; both + all_gather of partial points"),
+                   "parallelism": "1 GPU" if world == 1 else (f"resident leg: inputs replicated, {W_plan} windows sharded over {world} GPUs, one NCCL all_gather of the window "
+                                                                  f"digits + one host pass; e2e leg: points sharded over {world} GPUs + all_gather of partial points"),
                    "window_c": st["c"], "windows": st["num_windows"],
                    "l2": "no flush needed: inputs (128 MiB) + sort/bucket scratch (~470 MiB) exceed the 126 MB L2"},
         "point_adds_per_s": padds / (ms_res * 1e-3), "Mop_point_adds_per_s": padds / (ms_res * 1e-3) / 1e6,

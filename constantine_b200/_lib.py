@@ -35,6 +35,10 @@ def load():
     vp, sz, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
     lib.ctt_b200_msm_device.argtypes = [ci, ci, vp, vp, vp, sz, ci, ci, ci, ci]
     lib.ctt_b200_msm_device.restype = ci
+    lib.ctt_b200_msm_device_digits.argtypes = [ci, vp, vp, vp, sz, ci, ci, ci, ci]
+    lib.ctt_b200_msm_device_digits.restype = ci
+    lib.ctt_b200_combine_window_digits.argtypes = [ci, ci, vp, vp, ci, ci]
+    lib.ctt_b200_combine_window_digits.restype = ci
     lib.ctt_b200_msm_host.argtypes = [ci, ci, vp, vp, vp, sz, ci]
     lib.ctt_b200_msm_host.restype = ci
     lib.ctt_b200_sum_partials.argtypes = [ci, ci, vp, vp, sz]

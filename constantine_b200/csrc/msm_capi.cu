@@ -49,6 +49,26 @@ int ctt_b200_msm_device(int curve_id, int out_kind, void* r, const void* d_coefs
   return -1;
 }
 
+int ctt_b200_msm_device_digits(int curve_id, void* d_digits_out, const void* d_coefs, const void* d_points, size_t len, int fr_mont,
+                               int force_c, int win_begin, int win_end) {
+  switch (curve_id) {
+#define X(ID, DESC) case ID: return msm_dev_digits<DESC>(d_digits_out, d_coefs, d_points, len, fr_mont != 0, force_c, win_begin, win_end);
+    B200_FOR_EACH_CURVE(X)
+#undef X
+  }
+  return -1;
+}
+
+int ctt_b200_combine_window_digits(int curve_id, int out_kind, void* r, const void* h_digits, int c, int num_windows) {
+  if (c < 2 || c > 20 || num_windows < 0) return -1;
+  switch (curve_id) {
+#define X(ID, DESC) case ID: combine_window_digits<DESC>(r, h_digits, c, num_windows, out_kind); return 0;
+    B200_FOR_EACH_CURVE(X)
+#undef X
+  }
+  return -1;
+}
+
 int ctt_b200_msm_host(int curve_id, int out_kind, void* r, const void* coefs, const void* points, size_t len, int fr_mont) {
   switch (curve_id) {
 #define X(ID, DESC) case ID: msm_host<DESC>(r, coefs, points, len, fr_mont != 0, out_kind); return 0;

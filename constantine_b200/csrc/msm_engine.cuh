@@ -336,6 +336,32 @@ inline int auto_affine_levels(size_t entries, size_t nbuckets, size_t batch) {
   return levels;
 }
 
+// ---- host tail over radix-16 window digits --------------------------------------------------------------------
+// parts[w * groups + g] = D_{w,g} with  S_w = sum_g 16^g D_{w,g}  (k_plane_combine); returns sum_w 2^(c * (wshift + w)) S_w.
+// One doubling per bit position from the top, one addition per non-empty digit (reference ec_multi_scalar_mul_parallel.nim:198-203
+// does c doublings + one addition per window).
+template <class H>
+host::HXyzz<H> horner_window_digits(const host::HXyzz<H>* parts, int nw, int groups, int c, int wshift) {
+  using HP = host::HXyzz<H>;
+  HP r = HP::inf();
+  if (nw <= 0 || groups <= 0) return r;
+  const int emax = c * (wshift + nw - 1) + 4 * (groups - 1);
+  static thread_local std::vector<HP> by_exp;
+  by_exp.assign((size_t)emax + 1, HP::inf());
+  for (int w = 0; w < nw; w++)
+    for (int g = 0; g < groups; g++) {
+      const HP& pt = parts[(size_t)w * groups + g];
+      if (pt.is_inf()) continue;
+      const int e = c * (wshift + w) + 4 * g;
+      by_exp[e] = host::xyzz_add(by_exp[e], pt);
+    }
+  for (int e = emax; e >= 0; e--) {
+    r = host::xyzz_dbl(r);
+    if (!by_exp[e].is_inf()) r = host::xyzz_add(r, by_exp[e]);
+  }
+  return r;
+}
+
 // ---- one MSM on device-resident inputs ------------------------------------------------------------------------
 // d_scalars: n x 32 B, d_points: n affine points (ABI layout, Montgomery residues). Produces the window sums in pinned
 // host memory and runs the host tail. Window range [win_begin, win_end) lets several devices split one MSM by windows;
@@ -362,7 +388,7 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
                                       int force_c, int win_begin, int win_end, cudaEvent_t wait_points = nullptr,
                                       size_t table_stride = 0, size_t batch = 1, bool shared_points = false,
                                       host::HXyzz<typename C::H>* batch_out = nullptr,
-                                      const std::vector<InputChunk>* input_chunks = nullptr) {
+                                      const std::vector<InputChunk>* input_chunks = nullptr, void* d_digits_out = nullptr) {
   using T = typename C::T;
   using H = typename C::H;
   using HP = host::HXyzz<H>;
@@ -654,6 +680,16 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   }
   if (E.collect_timing) B200_CUDA_CHECK(cudaEventRecord(E.ev[5], s));
   static_assert(sizeof(HP) == XYZZ_BYTES, "host/device XYZZ layout");
+  if (d_digits_out) {
+    // multi-GPU window sharding: leave this device's radix-16 window digits in the caller's DEVICE buffer and return without
+    // synchronising -- the caller's collective (same stream) gathers every rank's digits and ONE host pass combines them
+    if (!plane_reduce) { fprintf(stderr, "[ctt_b200_msm] FATAL: device digits need the bit-plane reduction (single MSM, reduce mode 0)\n"); abort(); }
+    B200_CUDA_CHECK(cudaMemcpyAsync(d_digits_out, (const uint32_t*)E.red_planes.ptr + (size_t)nw * pr_planes * XW, (size_t)nw * pr_groups * XYZZ_BYTES,
+                                    cudaMemcpyDeviceToDevice, s));
+    st.kernel_launches = launches;
+    st.ms_total = 0;
+    return HP::inf();
+  }
   auto read_times = [&]() {
     if (!E.collect_timing) return;
     B200_CUDA_CHECK(cudaEventRecord(E.ev[6], s));
@@ -684,28 +720,12 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   // ec_multi_scalar_mul_parallel.nim:198-203: c doublings + one addition per window), including the shift by c*win_begin.
   HP r = HP::inf();
   if (plane_reduce) {
-    // window w arrives as radix-16 digits D_g of its sum, S_w = sum_g 16^g D_g: one doubling per bit position, one addition
-    // per digit
+    // window w arrives as radix-16 digits D_g of its sum, S_w = sum_g 16^g D_g
     const size_t out_bytes = (size_t)nw * pr_groups * XYZZ_BYTES;
     E.ensure_host(out_bytes);
     B200_CUDA_CHECK(cudaMemcpyAsync(E.h_result, (const uint32_t*)E.red_planes.ptr + (size_t)nw * pr_planes * XW, out_bytes, cudaMemcpyDeviceToHost, s));
     B200_CUDA_CHECK(cudaStreamSynchronize(s));
-    const HP* parts = reinterpret_cast<const HP*>(E.h_result);
-    const int wshift = table_mode ? 0 : plan.win_begin;
-    const int emax = c * (wshift + nw - 1) + 4 * ((int)pr_groups - 1);
-    static thread_local std::vector<HP> by_exp;
-    by_exp.assign((size_t)emax + 1, HP::inf());
-    for (int w = 0; w < nw; w++)
-      for (uint32_t g = 0; g < pr_groups; g++) {
-        const HP& pt = parts[(size_t)w * pr_groups + g];
-        if (pt.is_inf()) continue;
-        const int e = c * (wshift + w) + 4 * (int)g;
-        by_exp[e] = host::xyzz_add(by_exp[e], pt);
-      }
-    for (int e = emax; e >= 0; e--) {
-      r = host::xyzz_dbl(r);
-      if (!by_exp[e].is_inf()) r = host::xyzz_add(r, by_exp[e]);
-    }
+    r = horner_window_digits<H>(reinterpret_cast<const HP*>(E.h_result), nw, (int)pr_groups, c, table_mode ? 0 : plan.win_begin);
   } else {
     // per-window partial sums (<= 4 each) -> host; finish the sums there
     const size_t out_bytes = (size_t)nw * row * XYZZ_BYTES;
@@ -1041,6 +1061,28 @@ void msm_dev_ptrs(void* r_out, const void* d_coefs, const void* d_points, size_t
   E.stats.ms_h2d = 0;
   HP r = msm_device<C>(E, d_coefs, d_points, len, fr_mont, force_c, win_begin, win_end, nullptr, table_stride);
   thread_stats() = E.stats;
+  write_result<C>(r_out, r, kind);
+}
+
+// window-sharded multi-GPU leg: digits of this device's window range stay on the device (no synchronisation); returns the
+// number of digits per window
+template <class C>
+int msm_dev_digits(void* d_digits_out, const void* d_coefs, const void* d_points, size_t len, bool fr_mont, int force_c, int win_begin,
+                   int win_end) {
+  EngineLease lease = acquire_engine();
+  Engine& E = *lease.e;
+  E.stats.ms_h2d = 0;
+  msm_device<C>(E, d_coefs, d_points, len, fr_mont, force_c, win_begin, win_end, nullptr, 0, 1, false, nullptr, nullptr, d_digits_out);
+  thread_stats() = E.stats;
+  return (E.stats.c - 1 + 3) / 4;
+}
+
+// digits of ALL windows 0 .. num_windows-1 (window-major, ceil((c-1)/4) per window, host memory) -> the MSM result
+template <class C>
+void combine_window_digits(void* r_out, const void* h_digits, int c, int num_windows, int kind) {
+  using HP = host::HXyzz<typename C::H>;
+  const int groups = (c - 1 + 3) / 4;
+  HP r = horner_window_digits<typename C::H>(reinterpret_cast<const HP*>(h_digits), num_windows, groups, c, 0);
   write_result<C>(r_out, r, kind);
 }
 

@@ -199,6 +199,8 @@ void* run_precompute_table(const void* d_points, size_t n, int c, int* W_out) {
 #define B200_INSTANTIATE_CURVE(DESC)                                                                              \
   template void msm_host<DESC>(void*, const void*, const void*, size_t, bool, int);                               \
   template void msm_dev_ptrs<DESC>(void*, const void*, const void*, size_t, bool, int, int, int, int, size_t);    \
+  template int msm_dev_digits<DESC>(void*, const void*, const void*, size_t, bool, int, int, int);               \
+  template void combine_window_digits<DESC>(void*, const void*, int, int, int);                                  \
   template void* run_precompute_table<DESC>(const void*, size_t, int, int*);                                      \
   template void msm_cached<DESC>(void*, const void*, const void*, size_t, bool, int, int, size_t);                \
   template void msm_batch_host<DESC>(void*, const void*, const void*, size_t, size_t, bool, int, bool);           \
@@ -210,6 +212,8 @@ void* run_precompute_table(const void* d_points, size_t n, int c, int* W_out) {
 #define B200_DECLARE_CURVE(DESC)                                                                                  \
   extern template void msm_host<DESC>(void*, const void*, const void*, size_t, bool, int);                        \
   extern template void msm_dev_ptrs<DESC>(void*, const void*, const void*, size_t, bool, int, int, int, int, size_t); \
+  extern template int msm_dev_digits<DESC>(void*, const void*, const void*, size_t, bool, int, int, int);        \
+  extern template void combine_window_digits<DESC>(void*, const void*, int, int, int);                           \
   extern template void* run_precompute_table<DESC>(const void*, size_t, int, int*);                               \
   extern template void msm_cached<DESC>(void*, const void*, const void*, size_t, bool, int, int, size_t);         \
   extern template void msm_batch_host<DESC>(void*, const void*, const void*, size_t, size_t, bool, int, bool);    \

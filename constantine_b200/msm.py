@@ -107,6 +107,30 @@ def msm_device_ptrs(curve, d_coefs: int, d_points: int, n: int, out=OUT_JAC, fr_
     return r.raw
 
 
+def digits_per_window(c: int) -> int:
+    """radix-16 digits of a window sum (k_plane_combine): ceil((c - 1) / 4)."""
+    return (c - 1 + 3) // 4
+
+
+def msm_device_digits(curve, d_digits_out: int, d_coefs: int, d_points: int, n: int, fr_mont=False, force_c=0, win_begin=0, win_end=-1) -> int:
+    """Window range [win_begin, win_end) of an MSM over device-resident inputs; the radix-16 digits of the window sums stay in the
+    device buffer d_digits_out (raw XYZZ, window-major). NOT synchronised: order later work on the engine's stream."""
+    cv = _curve(curve)
+    g = _lib.load().ctt_b200_msm_device_digits(cv.curve_id, d_digits_out, d_coefs, d_points, n, int(fr_mont), force_c, win_begin, win_end)
+    if g < 0:
+        raise ValueError("ctt_b200_msm_device_digits failed")
+    return g
+
+
+def combine_window_digits(curve, h_digits, c: int, num_windows: int, out=OUT_JAC) -> bytes:
+    """digits of all windows 0..num_windows-1 (host buffer, window-major, digits_per_window(c) XYZZ points each) -> result struct."""
+    cv = _curve(curve)
+    r = ctypes.create_string_buffer(cv.coord_bytes * (4 if out == OUT_XYZZ else 3))
+    if _lib.load().ctt_b200_combine_window_digits(cv.curve_id, out, r, _buf(h_digits), c, num_windows) != 0:
+        raise ValueError("ctt_b200_combine_window_digits failed")
+    return r.raw
+
+
 def sum_partials(curve, partials: bytes, count: int, out=OUT_JAC) -> bytes:
     cv = _curve(curve)
     size = cv.coord_bytes * (4 if out == OUT_XYZZ else 3)

@@ -93,6 +93,58 @@ def msm_sharded_device(curve, d_coefs: int, d_points: int, n_local: int, group=N
     return msm_point_sharded(cv, part, group=group, device=device, out=out)
 
 
+_digit_cache = {}
+
+
+def msm_window_sharded_device(curve, d_coefs: int, d_points: int, n: int, c: int, num_windows: int, group=None, device=None,
+                              out=_msm.OUT_JAC, fr_mont=False, local_digits: Optional[Callable] = None) -> bytes:
+    """North-star window sharding with ONE exchange and ONE host pass: every rank holds all n pairs, runs the engine for its
+    window range and leaves the radix-16 digits of its window sums on the device (no synchronisation, no per-rank host tail);
+    one all_gather (NCCL on the engine's stream) collects the <= world x ceil(W / world) x ceil((c-1)/4) digit points, one
+    device-to-host copy brings them over, and one Horner pass over the 255 bit positions finishes the MSM on every rank.
+    `local_digits(curve, wb, we) -> bytes` lets the CPU tests substitute the engine (gloo, host tensors)."""
+    import torch
+    import torch.distributed as dist
+    cv = curve if isinstance(curve, CurveParams) else CURVES[curve]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    groups = _msm.digits_per_window(c)
+    xyzz = 4 * cv.coord_bytes
+    per_rank_windows = -(-num_windows // world)
+    blk = per_rank_windows * groups * xyzz                     # fixed-size payload; unused slots stay zero = infinity
+    wb, we = window_range(num_windows, world, rank)
+    key = (blk, world, str(device), id(group))
+    bufs = _digit_cache.get(key)
+    if bufs is None:
+        if device is None:
+            bufs = (torch.zeros(blk, dtype=torch.uint8), torch.zeros(world * blk, dtype=torch.uint8), None)
+        else:
+            bufs = (torch.zeros(blk, dtype=torch.uint8, device=device), torch.zeros(world * blk, dtype=torch.uint8, device=device),
+                    torch.zeros(world * blk, dtype=torch.uint8).pin_memory())
+        _digit_cache[key] = bufs
+    mine, everyone, h_all = bufs
+    if local_digits is None:
+        # the engine must launch on the stream the collective is issued on: stream order is the only synchronisation
+        from . import _lib
+        _lib.load().ctt_b200_set_stream(ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+        _msm.msm_device_digits(cv, mine.data_ptr(), d_coefs, d_points, n, fr_mont=fr_mont, force_c=c, win_begin=wb, win_end=we)
+        dist.all_gather_into_tensor(everyone, mine, group=group)
+        h_all.copy_(everyone, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+        raw = h_all.numpy()
+    else:
+        payload = local_digits(cv, wb, we)
+        mine.zero_()
+        mine.numpy()[:len(payload)] = memoryview(payload)
+        dist.all_gather(list(everyone.view(world, blk).unbind(0)), mine, group=group)
+        raw = everyone.numpy()
+    # ranks own consecutive window ranges: concatenating the used part of every block gives the global window-major order
+    parts = []
+    for g in range(world):
+        gb, ge = window_range(num_windows, world, g)
+        parts.append(raw[g * blk:g * blk + (ge - gb) * groups * xyzz].tobytes())
+    return _msm.combine_window_digits(cv, b"".join(parts), c, num_windows, out=out)
+
+
 def msm_batch_sharded(curve, coefs, points, batch: int, length: int, group=None, device=None, out=_msm.OUT_JAC,
                       coef_kind="big", shared_points=False, local_batch: Optional[Callable] = None) -> list:
     """`batch` independent MSMs of `length` terms split by member over the ranks of `group`; every rank returns all

@@ -11,9 +11,9 @@ SRC = os.path.join(ROOT, "tests", "c_api", "msm_smoke.c")
 LIBDIR = os.path.join(ROOT, "constantine_b200", "lib")
 
 
-def _build(tmp_path):
-    exe = str(tmp_path / "msm_smoke")
-    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), SRC,
+def _build(tmp_path, src=None, name="msm_smoke"):
+    exe = str(tmp_path / name)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), src or SRC,
                            "-L", LIBDIR, "-lctt_b200_msm", f"-Wl,-rpath,{LIBDIR}", "-o", exe])
     return exe
 
@@ -48,3 +48,21 @@ def test_c_program_result_matches_the_eip2537_vector(tmp_path, kat):
     case = next(c for c in kat["eip2537"] if c["name"] == "bls_g1multiexp_(g1+g1=2*g1)")
     want = (tuple(int(c, 16) for c in case["expected"][0]), tuple(int(c, 16) for c in case["expected"][1]))
     assert pyref.jac_bytes_to_affine(raw, cv) == want
+
+
+@pytest.mark.gpu
+def test_c_program_multi_gpu_behind_the_unchanged_symbol(tmp_path):
+    """tests/c_api/msm_multi_gpu.c: malloc'd inputs, the reference symbol once on one device and once with the device list set
+    (every visible GPU; one GPU listed twice on a one-GPU box) -- both equal the closed form [N (N + 1) / 2] G."""
+    exe = _build(tmp_path, os.path.join(ROOT, "tests", "c_api", "msm_multi_gpu.c"), "msm_multi_gpu")
+    n = 100000
+    out = subprocess.run([exe, str(n)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    toks = out.stdout.split()
+    assert toks[-2] == "devices" and int(toks[-1]) >= 2
+    limbs = [int(x, 16) for x in toks[:36]]
+    cv = CURVES["bls12_381_g1"]
+    want = pyref.ec_mul_fast(n * (n + 1) // 2 % cv.fr.modulus, cv.gen, cv)
+    for k in range(2):
+        raw = b"".join(v.to_bytes(8, "little") for v in limbs[18 * k:18 * k + 18])
+        assert pyref.jac_bytes_to_affine(raw, cv) == want, k

@@ -531,3 +531,35 @@ def test_forced_window_sizes_both_reduce_modes(M, lib):
             assert both == want, mode
     finally:
         lib.ctt_b200_set_reduce_mode(0)
+
+
+def test_window_digits_path_closed_form(M, lib):
+    """ctt_b200_msm_device_digits + ctt_b200_combine_window_digits (the multi-GPU window-sharded leg: digits of the window sums
+    stay on the device, one host pass at the end), here with the window ranges of 1, 2, 3 and 5 "ranks" run one after the
+    other on one GPU -- closed form; BLS12-381 G1 and Pallas."""
+    import torch
+    from constantine_b200 import sharded
+    for curve, n in (("bls12_381_g1", 50000), ("pallas_ec", 7001)):
+        cv = CURVES[curve]
+        rng = np.random.default_rng(n)
+        k = rng.integers(1, 2**63, size=n, dtype=np.uint64)
+        pts = _gen_points(lib, cv, k)
+        scal = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        scal[:, 31] &= (1 << (cv.scalar_bits - 248)) - 1
+        s_int = [int.from_bytes(scal[i].tobytes(), "little") for i in range(n)]
+        want = pyref.ec_mul_fast(sum(s * int(kk) for s, kk in zip(s_int, k)) % cv.fr.modulus, cv.gen, cv)
+        d_s, d_p = torch.from_numpy(scal).cuda(), torch.from_numpy(pts).cuda()
+        c, W = M.plan(cv, n)
+        groups = M.digits_per_window(c)
+        xyzz = 4 * cv.coord_bytes
+        for world in (1, 2, 3, 5):
+            parts = []
+            for rank in range(world):
+                wb, we = sharded.window_range(W, world, rank)
+                buf = torch.zeros((we - wb) * groups * xyzz, dtype=torch.uint8, device="cuda")
+                torch.cuda.synchronize()          # the engine writes the buffer from its own stream
+                assert M.msm_device_digits(cv, buf.data_ptr(), d_s.data_ptr(), d_p.data_ptr(), n, force_c=c, win_begin=wb, win_end=we) == groups
+                torch.cuda.synchronize()
+                parts.append(buf.cpu().numpy().tobytes())
+            got = M.combine_window_digits(cv, b"".join(parts), c, W)
+            assert pyref.jac_bytes_to_affine(got, cv) == want, (curve, world)

@@ -60,6 +60,24 @@ def _worker(rank, world, port, mode, q):
             wants = [pyref.msm_naive_fast(bks[i * m:(i + 1) * m], bpts[i * m:(i + 1) * m], cv) for i in range(batch)]
             q.put((rank, [pyref.jac_bytes_to_affine(r, cv) for r in res] == wants))
             return
+        elif mode == "window_digits":   # north-star window sharding: digits of the window sums, one exchange, one host pass
+            c = 8
+            W = 255 // c + 1
+            groups = M.digits_per_window(c)
+
+            def local_digits(cvv, wb, we):   # stands in for ctt_b200_msm_device_digits: D_0 = S_w, the other digits empty
+                out = b""
+                for w in range(wb, we):
+                    sw = None
+                    for k, P in zip(ks, pts):
+                        val, neg = oracle.signed_digit(k, 255, c, w)
+                        if val:
+                            term = pyref.ec_mul_fast(val, P, cvv)
+                            sw = pyref.ec_add(sw, pyref.ec_neg(term, cvv) if neg else term, cvv)
+                    out += affine_to_xyzz_bytes(sw, cvv) + bytes(4 * cvv.coord_bytes) * (groups - 1)
+                return out
+
+            got = sharded.msm_window_sharded_device(cv, 0, 0, n, c, W, local_digits=local_digits)
         else:  # window sharding: every rank holds all pairs, owns a window range, returns sum 2^(cw) S_w over its range
             c = 8
             W = 255 // c + 1
@@ -81,7 +99,7 @@ def _worker(rank, world, port, mode, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["points", "windows", "bank"])
+@pytest.mark.parametrize("mode", ["points", "windows", "window_digits", "bank"])
 def test_two_rank_sharded_msm(mode):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
