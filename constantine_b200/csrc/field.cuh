@@ -724,7 +724,14 @@ struct Fp2 {
     r.c1 = t + t;
     return r;
   }
+  // B200_FP2_CALL (experiment, default off): the three base-field products of an Fp2 product go through the out-of-line
+  // multiplier (Fp::mul_call) even in the hot mixed add -- 27 inlined 381-bit multipliers per mixed add spill registers and
+  // overflow the instruction caches.
+#ifndef B200_FP2_CALL
+#define B200_FP2_CALL 0
+#endif
   B200_DEV Fp2 mul_u(const Fp2& b) const {
+    if constexpr (B200_FP2_CALL && N >= 12) return (*this) * b;
     Base v0 = c0.mul_u(b.c0);
     Base v1 = c1.mul_u(b.c1);
     Base s = (c0 + c1).mul_u(b.c0 + b.c1);
@@ -734,6 +741,7 @@ struct Fp2 {
     return r;
   }
   B200_DEV Fp2 sqr_u() const {
+    if constexpr (B200_FP2_CALL && N >= 12) return sqr();
     Base t = c0.mul_u(c1);
     Fp2 r;
     r.c0 = (c0 + c1).mul_u(c0 - c1);

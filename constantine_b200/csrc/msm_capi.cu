@@ -88,16 +88,16 @@ int ctt_b200_sum_partials(int curve_id, int out_kind, void* r, const void* parti
 }
 
 int ctt_b200_plan(int curve_id, size_t len, int force_c, int* c, int* num_windows) {
-  int bits = 0;
+  int bits = 0, words = 12;
   switch (curve_id) {
-#define X(ID, DESC) case ID: bits = DESC::SCALAR_BITS; break;
+#define X(ID, DESC) case ID: bits = DESC::SCALAR_BITS; words = DESC::T::WORDS; break;
     B200_FOR_EACH_CURVE(X)
 #undef X
     default: return -1;
   }
   int tuned_c;
   { std::lock_guard<std::mutex> lock(config().mu); tuned_c = config().tuning.force_c; }
-  int cc = force_c > 0 ? force_c : (tuned_c > 0 ? tuned_c : choose_window(len, bits));
+  int cc = force_c > 0 ? force_c : (tuned_c > 0 ? tuned_c : choose_window(len, bits, words));
   if (cc < 2) cc = 2;
   if (cc > 20) cc = 20;
   *c = cc;

@@ -81,19 +81,20 @@ struct Stats {               // filled per call; read back through ctt_b200_last
 };
 
 // Window size: minimise  W*N*MADD + W*2^(c-1)*REDUCE  (same shape as the reference's bestBucketBitSize cost,
-// reference ec_multi_scalar_mul_scheduler.nim:172-223, with weights measured on B200: one bucket of the reduction costs
-// about as much as 8 accumulated entries).
-inline int choose_window(size_t n, int bits, int num_devices_windows = 1) {
+// reference ec_multi_scalar_mul_scheduler.nim:172-223, with weights measured on B200, round 2: an accumulated entry costs
+// ~0.32 ns, a bucket of the bit-plane reduction ~1.3 ns on top of a fixed ~0.3 ms; the ratio below reproduces the measured
+// optima c = 13 / 15 / 16 at N = 2^16 / 2^18 / 2^20 for BLS12-381 G1, profiles/sweep_c_r2.jsonl).
+inline int choose_window(size_t n, int bits, int coord_words = 12) {
   double best = 1e300;
   int best_c = 2;
   for (int c = 2; c <= 20; c++) {
     int W = bits / c + 1;
     double acc = (double)W * (double)n * 10.0;
-    double red = (double)W * (double)(1u << (c - 1)) * 80.0;   // measured: ~3.1 ns per bucket vs ~0.39 ns per accumulated entry
+    // Fp2 coordinates: the reduction is a chain of dependent Fp2 point operations -- relatively dearer (measured optimum c = 13 at 2^18)
+    double red = (double)W * (double)(1u << (c - 1)) * (coord_words > 12 ? 60.0 : 24.0);
     double cost = acc + red;
     if (cost < best) { best = cost; best_c = c; }
   }
-  (void)num_devices_windows;
   return best_c;
 }
 
@@ -327,12 +328,18 @@ inline Stats& thread_stats() {
 
 // Batched-affine levels pay when a thread's batch is long enough to amortise its inversion (level size / resident threads)
 // and the runs are long enough to have levels at all: large single MSMs. Small / batched calls stay on the XYZZ path.
-inline int auto_affine_levels(size_t entries, size_t nbuckets, size_t batch) {
-  if (batch > 1 || entries < (1ull << 22) || nbuckets == 0) return 0;
+// Measured break-even (profiles/bench_affine_r2_*.jsonl, sweep_c_r2.jsonl): 381-bit G1 from ~2^23 sorted entries (N = 2^20: 8.35 ->
+// 7.27 ms; N = 2^18: slower), 256-bit G1 from ~2^25 (an inversion costs relatively more next to a 136-MAC multiplication), Fp2 from
+// 2^22 (the inversion stays in Fp while every saved multiplication is three of them: N = 2^18 G2 12.9 -> 8.4 ms with four levels).
+inline int auto_affine_levels(size_t entries, size_t nbuckets, size_t batch, int coord_words) {
+  if (batch > 1 || nbuckets == 0) return 0;
+  const bool ext = coord_words > 12;
+  const size_t min_entries = ext ? (1ull << 22) : (coord_words > 8 ? (1ull << 23) : (1ull << 25));
+  if (entries < min_entries) return 0;
   const double mean_run = (double)entries / (double)nbuckets;
+  const int cap = ext ? 4 : 3;
   int levels = 0;
-  while (levels < 4 && mean_run >= (double)(4u << levels)) levels++;   // mean run 32 -> 4 levels... capped below
-  if (levels > 3) levels = 3;
+  while (levels < cap && mean_run >= (double)(4u << levels)) levels++;   // mean run 32 -> 3 levels, 64 -> 4
   return levels;
 }
 
@@ -407,7 +414,7 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   const bool table_mode = table_stride > 0;
   if (input_chunks && (batch > 1 || table_mode || input_chunks->empty())) input_chunks = nullptr;
 
-  int c = force_c > 0 ? force_c : (E.tuning.force_c > 0 ? E.tuning.force_c : choose_window(n, C::SCALAR_BITS));
+  int c = force_c > 0 ? force_c : (E.tuning.force_c > 0 ? E.tuning.force_c : choose_window(n, C::SCALAR_BITS, T::WORDS));
   if (c < 2) c = 2;
   if (c > 20) c = 20;
   DigitPlan plan = make_plan(C::SCALAR_BITS, c, win_begin, win_end);
@@ -454,7 +461,7 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
 
     // batched-affine levels: the XYZZ accumulation then runs over the survivor list only
     int AL = E.tuning.affine_levels;
-    if (AL < 0) AL = auto_affine_levels(entries, nbuckets, batch);
+    if (AL < 0) AL = auto_affine_levels(entries, nbuckets, batch, T::WORDS);
     if (entries >= (1ull << 31) || nbuckets >= (1ull << 30)) AL = 0;
     if (AL > AFF_MAX_LEVELS) AL = AFF_MAX_LEVELS;
     // level r holds sum_b ceil(n_b / 2^r) <= entries / 2^r + nbuckets slots

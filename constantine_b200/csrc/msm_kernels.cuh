@@ -142,20 +142,41 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
   if (live) {
     // software pipeline: the (key, ref, point) of entry j+1 is fetched before the point addition of entry j is issued,
     // so the dependent gather keys -> vals -> points overlaps ~10 field multiplications instead of stalling the warp.
+    // The next point is held in registers. For Fp2 (a point is 48 words, the accumulator 96) the live set of a mixed addition
+    // exceeds the 255-register file either way (ptxas spills ~0.6 KB to local memory, L1-resident); -DB200_FP2_REG_PREFETCH=0
+    // pulls the next point into L2 only and loads it at the top of its own iteration instead.
+#ifndef B200_FP2_REG_PREFETCH
+#define B200_FP2_REG_PREFETCH 1
+#endif
+    constexpr bool REG_PREFETCH = T::WORDS <= 12 || B200_FP2_REG_PREFETCH;
     uint32_t key_n = (base < total) ? keys[base] : no_key;
     uint32_t v_n = 0;
     Aff<T> p_n;
-    p_n.x = T::zero(); p_n.y = T::zero();
-    if (key_n < no_key) { v_n = vals[base]; p_n = load_affine<T>(points, v_n & 0x7FFFFFFFu); }
+    if constexpr (REG_PREFETCH) { p_n.x = T::zero(); p_n.y = T::zero(); }
+    if (key_n < no_key) {
+      v_n = vals[base];
+      if constexpr (REG_PREFETCH) p_n = load_affine<T>(points, v_n & 0x7FFFFFFFu);
+    }
 #pragma unroll 1
     for (int j = 0; j < K; j++) {
       const uint32_t key = key_n;
       if (key >= no_key) break;  // zero digits are sorted to the tail (or end of list): nothing left in this slice
       const uint32_t v = v_n;
-      Aff<T> p = p_n;
+      Aff<T> p;
+      if constexpr (REG_PREFETCH) p = p_n;
       const size_t nidx = base + j + 1;
       key_n = (j + 1 < K && nidx < total) ? keys[nidx] : no_key;
-      if (key_n < no_key) { v_n = vals[nidx]; p_n = load_affine<T>(points, v_n & 0x7FFFFFFFu); }
+      if (key_n < no_key) {
+        v_n = vals[nidx];
+        if constexpr (REG_PREFETCH) p_n = load_affine<T>(points, v_n & 0x7FFFFFFFu);
+        else {
+          const uint32_t* nx = points + (size_t)(v_n & 0x7FFFFFFFu) * (2 * T::WORDS);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 32));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 2 * T::WORDS - 1));
+        }
+      }
+      if constexpr (!REG_PREFETCH) p = load_affine<T>(points, v & 0x7FFFFFFFu);
       if (!p.is_inf()) p.y.cneg((v >> 31) != 0);
       if (key != cur_key) {
         if (cur_key != KEY_NONE) {
