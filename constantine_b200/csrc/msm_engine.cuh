@@ -91,7 +91,7 @@ inline int choose_window(size_t n, int bits, int coord_words = 12) {
     int W = bits / c + 1;
     double acc = (double)W * (double)n * 10.0;
     // Fp2 coordinates: the reduction is a chain of dependent Fp2 point operations -- relatively dearer (measured optimum c = 13 at 2^18)
-    double red = (double)W * (double)(1u << (c - 1)) * (coord_words > 12 ? 60.0 : 24.0);
+    double red = (double)W * (double)(1u << (c - 1)) * (coord_words > 12 ? 60.0 : 30.0);
     double cost = acc + red;
     if (cost < best) { best = cost; best_c = c; }
   }

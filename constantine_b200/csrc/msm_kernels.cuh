@@ -142,11 +142,11 @@ k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ val
   if (live) {
     // software pipeline: the (key, ref, point) of entry j+1 is fetched before the point addition of entry j is issued,
     // so the dependent gather keys -> vals -> points overlaps ~10 field multiplications instead of stalling the warp.
-    // The next point is held in registers. For Fp2 (a point is 48 words, the accumulator 96) the live set of a mixed addition
-    // exceeds the 255-register file either way (ptxas spills ~0.6 KB to local memory, L1-resident); -DB200_FP2_REG_PREFETCH=0
-    // pulls the next point into L2 only and loads it at the top of its own iteration instead.
+    // Single-field coordinates hold the next point in registers. For Fp2 (a point is 48 words, the accumulator 96) the live set of
+    // a mixed addition exceeds the 255-register file either way (ptxas spills ~0.6 KB to local memory, L1-resident), so the next
+    // point is only pulled into L2 and loaded at the top of its own iteration (-DB200_FP2_REG_PREFETCH=1 restores the register form).
 #ifndef B200_FP2_REG_PREFETCH
-#define B200_FP2_REG_PREFETCH 1
+#define B200_FP2_REG_PREFETCH 0
 #endif
     constexpr bool REG_PREFETCH = T::WORDS <= 12 || B200_FP2_REG_PREFETCH;
     uint32_t key_n = (base < total) ? keys[base] : no_key;
