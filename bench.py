@@ -392,7 +392,15 @@ def main():
         return
 
     st = stats[-1]
-    acc_ms = sum(s["ms_accumulate"] for s in serial_stats) / len(serial_stats)
+    if world > 1:
+        # the window-digit leg returns without per-rank timing (no synchronisation inside the engine): take the phase times of
+        # this rank's window range from three extra calls of the synchronous device entry
+        serial_stats = []
+        for _ in range(3):
+            M.msm_device_ptrs(cv, d_scal.data_ptr(), d_pts.data_ptr(), n, out=M.OUT_XYZZ, force_c=c_plan, win_begin=wb, win_end=we)
+            serial_stats.append(M.last_stats())
+        st = serial_stats[-1]
+    acc_ms = max(1e-6, sum(s["ms_accumulate"] for s in serial_stats) / len(serial_stats))
     madds = st["entries"]      # bucket point-adds issued by k_accumulate per launch (one per sorted entry, minus run heads)
     macs = madds * INT_MACS_PER_POINT_ADD
     achieved = macs / (acc_ms * 1e-3)

@@ -781,22 +781,23 @@ void write_result(void* r_out, const host::HXyzz<typename C::H>& p, int kind) {
 struct HostCopyPool {
   struct Slot {
     std::thread th;
+    std::mutex claim;                  // held by the caller that is using this helper
     std::mutex m;
     std::condition_variable cv;
     char* dst = nullptr; const char* src = nullptr; size_t bytes = 0;
     bool has_job = false, done = true;
   };
-  std::mutex mu;                       // one staged copy at a time uses the helpers
+  std::mutex mu;                       // guards creation only; concurrent callers share the helpers that are free
   std::vector<Slot*> slots;
   int threads = 0;
   void ensure() {
+    std::lock_guard<std::mutex> lk(mu);
     if (threads) return;
     int t = 6;
     if (const char* v = getenv("CTT_B200_STAGE_THREADS")) t = atoi(v);
     const int hw = (int)std::thread::hardware_concurrency();
     if (hw > 0 && t > hw) t = hw;
     if (t < 1) t = 1;
-    threads = t;
     for (int i = 0; i + 1 < t; i++) {
       Slot* sl = new Slot;
       sl->th = std::thread([sl] {
@@ -815,25 +816,31 @@ struct HostCopyPool {
       sl->th.detach();
       slots.push_back(sl);
     }
+    threads = t;
   }
-  // dst <- src, split evenly over the helpers and the calling thread
+  // dst <- src, split evenly over the calling thread and the helpers that are free right now (several devices' workers may
+  // stage at the same time; each takes what it can get)
   void copy(void* dst, const void* src, size_t bytes) {
-    const size_t parts = (size_t)threads;
-    if (parts <= 1 || bytes < (1u << 20)) { memcpy(dst, src, bytes); return; }
+    if (threads <= 1 || bytes < (1u << 20)) { memcpy(dst, src, bytes); return; }
+    Slot* mine[16];
+    size_t got = 0;
+    for (size_t i = 0; i < slots.size() && got < 16; i++)
+      if (slots[i]->claim.try_lock()) mine[got++] = slots[i];
+    const size_t parts = got + 1;
     const size_t per = ((bytes / parts) + 4095) & ~(size_t)4095;
-    size_t off = 0;
-    size_t used = 0;
-    for (; used < slots.size() && off + per < bytes; used++, off += per) {
-      Slot* sl = slots[used];
+    size_t off = 0, used = 0;
+    for (; used < got && off + per < bytes; used++, off += per) {
+      Slot* sl = mine[used];
       { std::lock_guard<std::mutex> lk(sl->m); sl->dst = (char*)dst + off; sl->src = (const char*)src + off; sl->bytes = per; sl->has_job = true; sl->done = false; }
       sl->cv.notify_all();
     }
     memcpy((char*)dst + off, (const char*)src + off, bytes - off);
     for (size_t i = 0; i < used; i++) {
-      Slot* sl = slots[i];
+      Slot* sl = mine[i];
       std::unique_lock<std::mutex> lk(sl->m);
       sl->cv.wait(lk, [&] { return sl->done; });
     }
+    for (size_t i = 0; i < got; i++) mine[i]->claim.unlock();
   }
 };
 inline HostCopyPool& host_copy_pool() {
@@ -900,9 +907,7 @@ host::HXyzz<typename C::H> msm_host_on(int device, const void* coefs, const void
     r = msm_device<C>(E, E.d_scalars.ptr, E.d_points.ptr, len, fr_mont, 0, 0, -1, nullptr, 0, 1, false, nullptr, &chunks);
   } else if (sbytes + pbytes >= (8u << 20) && (is_pageable_host_memory(coefs) || is_pageable_host_memory(points))) {
     // pageable caller memory: stage it (scalars first, then the points) through the pinned double buffer
-    HostCopyPool& pool = host_copy_pool();
-    std::lock_guard<std::mutex> lk(pool.mu);
-    pool.ensure();
+    host_copy_pool().ensure();
     E.ensure_stage();
     int piece = 0;
     staged_h2d(E, E.d_scalars.ptr, coefs, sbytes, E.copy_stream, piece);
