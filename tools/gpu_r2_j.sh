@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/r2j_gpus.txt
 run() {  # curve logn ngpu
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $3 --master-addr 127.0.0.1 --master-port $((29700 + $3)) bench.py --gpus $3 --steps 8 --warmup 3 --curve $1 --logn $2 --no-cpu-baseline > gpurun_out/bench_r2_${1}_${2}_${3}gpu.json 2> gpurun_out/bench_r2_${1}_${2}_${3}gpu.err
+  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $3 --master-addr 127.0.0.1 --master-port $((29700 + $3)) bench.py --gpus $3 --steps 8 --warmup 3 --curve $1 --logn $2 --no-cpu-baseline > gpurun_out/bench_r2_${1}_${2}_${3}gpu.json 2> gpurun_out/bench_r2_${1}_${2}_${3}gpu.err
   python - <<PY
 import json
 try:
@@ -19,4 +19,4 @@ run pallas_ec 22 8
 run bls12_381_g2 18 8
 run bls12_381_g2 18 4
 run bls12_381_g2 18 2
-timeout 600 python tools/bench_multi_device.py --reps 6 > gpurun_out/multi_device_r2j.jsonl 2> gpurun_out/multi_device_r2j.err; cat gpurun_out/multi_device_r2j.jsonl; tail -2 gpurun_out/multi_device_r2j.err
+timeout 240 python tools/bench_multi_device.py --reps 6 > gpurun_out/multi_device_r2j.jsonl 2> gpurun_out/multi_device_r2j.err; cat gpurun_out/multi_device_r2j.jsonl; tail -2 gpurun_out/multi_device_r2j.err
