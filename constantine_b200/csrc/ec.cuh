@@ -116,6 +116,22 @@ B200_DEV Xyzz<T> xyzz_dbl_affine(const Aff<T>& p) {
 // 2*P, dbl-2008-s-1 with a = 0
 template <class T>
 B200_DEV Xyzz<T> xyzz_dbl(const Xyzz<T>& p) {
+  if constexpr (T::HAS_MUL2) {
+    // the same formulas with independent products paired (T::mul2_call): 9 multiplications in 5 dependent steps
+    T U = p.y.dbl();
+    T V = U * U;
+    auto ws = T::mul2_call(U, V, p.x, V);                 // W = U V, S = X V
+    auto xz = T::mul2_call(p.x, p.x, V, p.zz);            // X^2, ZZ3 = V ZZ
+    T M = xz.a.dbl() + xz.a;
+    auto mz = T::mul2_call(M, M, ws.a, p.zzz);            // M^2, ZZZ3 = W ZZZ
+    Xyzz<T> r;
+    r.x = mz.a - ws.b.dbl();
+    auto yy = T::mul2_call(M, ws.b - r.x, ws.a, p.y);     // M (S - X3), W Y
+    r.y = yy.a - yy.b;
+    r.zz = xz.b;
+    r.zzz = mz.b;
+    return r;
+  }
   T U = p.y.dbl();
   T V = U.sqr();
   T W = U * V;
@@ -190,6 +206,29 @@ template <class T>
 B200_DEV void xyzz_add(Xyzz<T>& acc, const Xyzz<T>& q) {
   if (q.is_inf()) return;
   if (acc.is_inf()) { acc = q; return; }
+  if constexpr (T::HAS_MUL2) {
+    // independent products paired: 14 multiplications in 8 dependent steps
+    auto u = T::mul2_call(acc.x, q.zz, q.x, acc.zz);       // U1, U2
+    auto sv = T::mul2_call(acc.y, q.zzz, q.y, acc.zzz);    // S1, S2
+    T P = u.b - u.a;
+    T R = sv.b - sv.a;
+    if (P.is_zero()) {
+      if (R.is_zero()) acc = xyzz_dbl_val(acc);
+      else acc = Xyzz<T>::inf();
+      return;
+    }
+    T PP = P * P;
+    auto pq = T::mul2_call(P, PP, u.a, PP);                // PPP, Q
+    auto rz = T::mul2_call(R, R, acc.zz, q.zz);            // R^2, ZZ1 ZZ2
+    T X3 = rz.a - pq.a - pq.b.dbl();
+    auto yz = T::mul2_call(R, pq.b - X3, sv.a, pq.a);      // R (Q - X3), S1 PPP
+    auto zz = T::mul2_call(rz.b, PP, acc.zzz, q.zzz);      // ZZ3, ZZZ1 ZZZ2
+    acc.x = X3;
+    acc.y = yz.a - yz.b;
+    acc.zz = zz.a;
+    acc.zzz = zz.b * pq.a;
+    return;
+  }
   T U1 = acc.x * q.zz;
   T U2 = q.x * acc.zz;
   T S1 = acc.y * q.zzz;

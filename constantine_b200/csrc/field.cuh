@@ -628,6 +628,21 @@ struct Fp {
 #define B200_MUL_VARIANT (-1)
 #endif
   static __device__ __noinline__ Fp mul_call(Fp a, Fp b) { Fp r; fe_mul<F>(r.l, a.l, b.l); return r; }
+  // Two INDEPENDENT products per call: the two unrolled carry-chain programs are interleaved by the scheduler, so a chain of
+  // dependent point operations (reduce / fix-up / tail kernels at low occupancy) pays ~1.3 multiplication latencies for two
+  // products instead of 2. Point formulas pair their independent products through this (ec.cuh).
+  struct Pair { Fp a, b; };
+#ifdef B200_NO_MUL2
+  static constexpr bool HAS_MUL2 = false;
+#else
+  static constexpr bool HAS_MUL2 = (N >= 12) && (B200_MUL_VARIANT < 0 || B200_MUL_VARIANT == 3);
+#endif
+  static __device__ __noinline__ Pair mul2_call(Fp a, Fp b, Fp c, Fp d) {
+    Pair r;
+    fe_mul<F>(r.a.l, a.l, b.l);
+    fe_mul<F>(r.b.l, c.l, d.l);
+    return r;
+  }
   B200_DEV Fp operator*(const Fp& b) const {
     constexpr int V = (B200_MUL_VARIANT >= 0) ? B200_MUL_VARIANT : (N >= 12 ? 3 : 0);
     if constexpr (V == 3) return mul_call(*this, b);
@@ -698,6 +713,7 @@ struct Fp2 {
   using Base = Fp<F>;
   static constexpr int N = F::N;
   static constexpr int WORDS = 2 * F::N;
+  static constexpr bool HAS_MUL2 = false;
   Base c0, c1;
 
   B200_DEV static Fp2 zero() { Fp2 r; r.c0 = Base::zero(); r.c1 = Base::zero(); return r; }

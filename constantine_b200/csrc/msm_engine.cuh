@@ -330,11 +330,12 @@ inline Stats& thread_stats() {
 // and the runs are long enough to have levels at all: large single MSMs. Small / batched calls stay on the XYZZ path.
 // Measured break-even (profiles/bench_affine_r2_*.jsonl, sweep_c_r2.jsonl): 381-bit G1 from ~2^23 sorted entries (N = 2^20: 8.35 ->
 // 7.27 ms; N = 2^18: slower), 256-bit G1 from ~2^25 (an inversion costs relatively more next to a 136-MAC multiplication), Fp2 from
-// 2^22 (the inversion stays in Fp while every saved multiplication is three of them: N = 2^18 G2 12.9 -> 8.4 ms with four levels).
+// 2^20 (the inversion stays in Fp while every saved multiplication is three of them: N = 2^18 G2 12.9 -> 7.8 ms with four levels; the
+// low threshold keeps the levels on for the window shards of a multi-GPU run).
 inline int auto_affine_levels(size_t entries, size_t nbuckets, size_t batch, int coord_words) {
   if (batch > 1 || nbuckets == 0) return 0;
   const bool ext = coord_words > 12;
-  const size_t min_entries = ext ? (1ull << 22) : (coord_words > 8 ? (1ull << 23) : (1ull << 25));
+  const size_t min_entries = ext ? (1ull << 20) : (coord_words > 8 ? (1ull << 23) : (1ull << 25));
   if (entries < min_entries) return 0;
   const double mean_run = (double)entries / (double)nbuckets;
   const int cap = ext ? 4 : 3;
@@ -395,7 +396,8 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
                                       int force_c, int win_begin, int win_end, cudaEvent_t wait_points = nullptr,
                                       size_t table_stride = 0, size_t batch = 1, bool shared_points = false,
                                       host::HXyzz<typename C::H>* batch_out = nullptr,
-                                      const std::vector<InputChunk>* input_chunks = nullptr, void* d_digits_out = nullptr) {
+                                      const std::vector<InputChunk>* input_chunks = nullptr, void* d_digits_out = nullptr,
+                                      const std::function<void()>* stage_points = nullptr) {
   using T = typename C::T;
   using H = typename C::H;
   using HP = host::HXyzz<H>;
@@ -525,7 +527,12 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
     // points of a host call arrive on the copy stream: nothing up to here reads them, and neither does the batched-affine plan
     // below (run bounds, level offsets, pair lists come from the sorted keys / refs alone), so the wait sits right in front of
     // the first kernel that gathers points
-    auto wait_for_points = [&]() { if (!input_chunks && ch.ready) B200_CUDA_CHECK(cudaStreamWaitEvent(s, ch.ready, 0)); };
+    // `stage_points` (pageable caller memory): the host-side staging of the points runs HERE in the call sequence, i.e. after digits,
+    // sort and plan have been queued, so the device works on the scalars while the host copies the points
+    auto wait_for_points = [&]() {
+      if (stage_points && *stage_points) (*stage_points)();
+      if (!input_chunks && ch.ready) B200_CUDA_CHECK(cudaStreamWaitEvent(s, ch.ready, 0));
+    };
     const void* acc_points = pts;
     if (AL) {
       const uint32_t nb = (uint32_t)nbuckets;
@@ -906,16 +913,21 @@ host::HXyzz<typename C::H> msm_host_on(int device, const void* coefs, const void
     B200_CUDA_CHECK(cudaEventRecord(t1, E.compute()));
     r = msm_device<C>(E, E.d_scalars.ptr, E.d_points.ptr, len, fr_mont, 0, 0, -1, nullptr, 0, 1, false, nullptr, &chunks);
   } else if (sbytes + pbytes >= (8u << 20) && (is_pageable_host_memory(coefs) || is_pageable_host_memory(points))) {
-    // pageable caller memory: stage it (scalars first, then the points) through the pinned double buffer
+    // pageable caller memory: stage it through the pinned double buffer -- the scalars first; the points only after digits, sort
+    // and the batched-affine plan have been queued (stage_points callback), so that the device is already busy meanwhile
     host_copy_pool().ensure();
     E.ensure_stage();
     int piece = 0;
     staged_h2d(E, E.d_scalars.ptr, coefs, sbytes, E.copy_stream, piece);
-    staged_h2d(E, E.d_points.ptr, points, pbytes, E.copy_stream, piece);
-    B200_CUDA_CHECK(cudaEventRecord(E.ev_points_ready, E.copy_stream));
-    B200_CUDA_CHECK(cudaStreamWaitEvent(E.compute(), E.ev_points_ready, 0));
+    B200_CUDA_CHECK(cudaEventRecord(E.ev_chunk[0], E.copy_stream));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(E.compute(), E.ev_chunk[0], 0));
     B200_CUDA_CHECK(cudaEventRecord(t1, E.compute()));
-    r = msm_device<C>(E, E.d_scalars.ptr, E.d_points.ptr, len, fr_mont, 0, 0, -1, nullptr);
+    const std::function<void()> stage = [&]() {
+      staged_h2d(E, E.d_points.ptr, points, pbytes, E.copy_stream, piece);
+      B200_CUDA_CHECK(cudaEventRecord(E.ev_points_ready, E.copy_stream));
+    };
+    // the event is recorded inside the callback, before the engine waits on it
+    r = msm_device<C>(E, E.d_scalars.ptr, E.d_points.ptr, len, fr_mont, 0, 0, -1, E.ev_points_ready, 0, 1, false, nullptr, nullptr, nullptr, &stage);
   } else {
     B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, sbytes, cudaMemcpyHostToDevice, E.compute()));
     B200_CUDA_CHECK(cudaMemcpyAsync(E.d_points.ptr, points, pbytes, cudaMemcpyHostToDevice, E.copy_stream));
