@@ -75,6 +75,8 @@ def load():
     lib.ctt_b200_set_reduce_mode.restype = None
     lib.ctt_b200_set_input_chunks.argtypes = [ci]
     lib.ctt_b200_set_input_chunks.restype = None
+    lib.ctt_b200_set_point_chunks.argtypes = [ci]
+    lib.ctt_b200_set_point_chunks.restype = None
     lib.ctt_b200_set_stream.argtypes = [vp]
     lib.ctt_b200_set_stream.restype = None
     lib.ctt_b200_sm_count.argtypes = []

@@ -201,6 +201,104 @@ B200_DEV T scratch_load(const uint4* scratch, size_t threads, size_t tid, uint32
   return v;
 }
 
+// ------------------------------------------------------------------------------------------------ level 0 by arrival of the points
+// A host call moves its points over PCIe in P chunks. A level-0 pair only needs the chunks of its own operands, so the pair list is
+// partitioned (stable counting sort, P <= 8 classes) by the LAST chunk a pair touches: launch q of the pair kernel runs as soon as
+// chunk q has landed, and only the last launch waits for the whole transfer.
+constexpr int PART_TILE = 1024, PART_THREADS = 256, PART_MAX = 8;
+
+B200_DEV uint32_t pair_chunk(const uint2 task, uint32_t n_points, uint32_t P) {
+  uint32_t idx = task.x & 0x7FFFFFFFu;
+  if (task.y != AFF_NONE) { const uint32_t j = task.y & 0x7FFFFFFFu; if (j > idx) idx = j; }
+  uint32_t q = (uint32_t)(((unsigned long long)idx * P) / n_points);
+  return q < P ? q : P - 1u;
+}
+
+// counts[q * nblk + blk] = slots of tile blk whose pair belongs to class q
+static __global__ void __launch_bounds__(PART_THREADS) k_part_count(const uint2* __restrict__ plan0, const uint32_t* __restrict__ total_ptr,
+                                                                    uint32_t n_points, uint32_t P, uint32_t nblk, uint32_t* counts) {
+  __shared__ uint32_t sm[PART_MAX];
+  if (threadIdx.x < PART_MAX) sm[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t total = *total_ptr;
+  const uint32_t base = blockIdx.x * PART_TILE;
+  uint32_t local[PART_MAX];
+#pragma unroll
+  for (int q = 0; q < PART_MAX; q++) local[q] = 0;
+  for (uint32_t i = threadIdx.x; i < PART_TILE; i += PART_THREADS) {
+    const uint32_t p = base + i;
+    if (p < total) {
+      const uint32_t q = pair_chunk(plan0[p], n_points, P);
+#pragma unroll
+      for (int k = 0; k < PART_MAX; k++) local[k] += (q == (uint32_t)k) ? 1u : 0u;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < PART_MAX; q++) {
+    uint32_t v = local[q];
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    if ((threadIdx.x & 31u) == 0 && v) atomicAdd(&sm[q], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < P) counts[threadIdx.x * nblk + blockIdx.x] = sm[threadIdx.x];
+}
+
+// one block: exclusive scan of counts in (class, tile) order, in place; starts[q] = first position of class q, starts[P] = total
+static __global__ void __launch_bounds__(SCAN_THREADS) k_part_scan(uint32_t* counts, uint32_t P, uint32_t nblk, uint32_t* starts) {
+  __shared__ uint32_t sm[SCAN_THREADS / 32 + 1];
+  uint32_t carry = 0;
+  const uint32_t len = P * nblk;
+  for (uint32_t base = 0; base < len; base += SCAN_THREADS) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = (i < len) ? counts[i] : 0u;
+    uint32_t tot;
+    const uint32_t ex = block_exclusive_scan(v, tot, sm);
+    if (i < len) {
+      counts[i] = carry + ex;
+      if (i % nblk == 0) starts[i / nblk] = carry + ex;
+    }
+    carry += tot;
+  }
+  if (threadIdx.x == 0) starts[P] = carry;
+}
+
+// perm[offset(class, tile) + rank within (class, tile)] = slot, ranks in slot order (stable)
+static __global__ void __launch_bounds__(PART_THREADS) k_part_scatter(const uint2* __restrict__ plan0, const uint32_t* __restrict__ total_ptr,
+                                                                      uint32_t n_points, uint32_t P, uint32_t nblk,
+                                                                      const uint32_t* __restrict__ offsets, uint32_t* perm) {
+  __shared__ uint32_t warp_cnt[PART_THREADS / 32][PART_MAX];
+  __shared__ uint32_t run_base[PART_MAX];
+  const uint32_t total = *total_ptr;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (threadIdx.x < PART_MAX) run_base[threadIdx.x] = (threadIdx.x < P) ? offsets[threadIdx.x * nblk + blockIdx.x] : 0u;
+  __syncthreads();
+  // the tile is walked in rounds of PART_THREADS consecutive slots so that ranks follow slot order
+  for (uint32_t round = 0; round < PART_TILE / PART_THREADS; round++) {
+    const uint32_t p = blockIdx.x * PART_TILE + round * PART_THREADS + threadIdx.x;
+    const bool live = p < total;
+    const uint32_t q = live ? pair_chunk(plan0[p], n_points, P) : 0xFFFFFFFFu;
+    uint32_t my_rank = 0;
+    for (uint32_t k = 0; k < P; k++) {
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, q == k);
+      if (q == k) my_rank = __popc(m & ((1u << lane) - 1u));
+      if (lane == 0) warp_cnt[warp][k] = __popc(m);
+    }
+    __syncthreads();
+    if (live) {
+      uint32_t before = 0;
+      for (unsigned w = 0; w < warp; w++) before += warp_cnt[w][q];
+      perm[run_base[q] + before + my_rank] = p;
+    }
+    __syncthreads();
+    if (threadIdx.x < P) {
+      uint32_t tot = 0;
+      for (unsigned w = 0; w < PART_THREADS / 32; w++) tot += warp_cnt[w][threadIdx.x];
+      run_base[threadIdx.x] += tot;
+    }
+    __syncthreads();
+  }
+}
+
 enum PairKind { PAIR_COPY1 = 0, PAIR_COPY2 = 1, PAIR_INF = 2, PAIR_ADD = 3, PAIR_DBL = 4 };
 
 // one slot's operands. FIRST: references into the caller's point array (sign in bit 31); else slots of the previous level.
@@ -277,10 +375,15 @@ B200_DEV void prefetch_point(const uint32_t* src, uint32_t ref) {
 // contiguous range of 32 M slots and lane l takes slots l, l + 32, ... of it (coalesced plans, outputs and level >= 1 operands).
 template <class T, bool FIRST>
 __global__ void __launch_bounds__(B200_AFF_THREADS, (T::WORDS <= 12) ? B200_AFF_MIN_BLOCKS : 1)
-k_affine_pairs(const void* __restrict__ plan, const uint32_t* __restrict__ total_ptr, const uint32_t* src, uint32_t* dst, uint4* scratch) {
+k_affine_pairs(const void* __restrict__ plan, const uint32_t* __restrict__ total_ptr, const uint32_t* src, uint32_t* dst, uint4* scratch,
+               const uint32_t* __restrict__ perm = nullptr, const uint32_t* __restrict__ range = nullptr) {
+  // perm / range (level 0 of a host call whose points arrive in chunks): this launch handles the slots perm[range[0] .. range[1]),
+  // i.e. the pairs whose operands all lie in the chunks that have arrived; otherwise slots 0 .. *total_ptr in order.
   const size_t threads = (size_t)gridDim.x * blockDim.x;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t total = *total_ptr;
+  const uint32_t range_begin = range ? range[0] : 0u;
+  const uint32_t total = range ? range[1] - range[0] : *total_ptr;
+  if (perm) perm += range_begin;
   const uint32_t M = (uint32_t)(((size_t)total + threads - 1) / threads);
   const unsigned lane = threadIdx.x & 31u;
   const size_t warp_base = (tid - lane) * (size_t)M;          // first slot of this warp
@@ -298,7 +401,8 @@ k_affine_pairs(const void* __restrict__ plan, const uint32_t* __restrict__ total
   // ---- pass 1: running product of the denominators; prefix products to the scratch
   T run = T::one();
   {
-    PairTask t_next = cnt ? load_task<FIRST>(plan, warp_base + lane) : PairTask{0u, AFF_NONE};
+    auto slot_of = [&](size_t t) -> size_t { return perm ? (size_t)perm[t] : t; };
+    PairTask t_next = cnt ? load_task<FIRST>(plan, slot_of(warp_base + lane)) : PairTask{0u, AFF_NONE};
     T x1n = T::zero(), x2n = T::zero();
     if (cnt) {
       x1n = load_x<T, FIRST>(src, t_next.a);
@@ -309,7 +413,7 @@ k_affine_pairs(const void* __restrict__ plan, const uint32_t* __restrict__ total
       const PairTask t = t_next;
       const T x1 = x1n, x2 = x2n;
       if (j + 1 < cnt) {
-        t_next = load_task<FIRST>(plan, warp_base + lane + 32u * (size_t)(j + 1));
+        t_next = load_task<FIRST>(plan, slot_of(warp_base + lane + 32u * (size_t)(j + 1)));
         x1n = load_x<T, FIRST>(src, t_next.a);
         if (t_next.b != AFF_NONE) x2n = load_x<T, FIRST>(src, t_next.b);
       }
@@ -331,14 +435,17 @@ k_affine_pairs(const void* __restrict__ plan, const uint32_t* __restrict__ total
   T inv = fe_inverse(run);
   // ---- pass 2: unwind, last slot first. The operands of slot j - 1 (found through its plan entry) and the prefix product it
   // will need are pulled into L2 while slot j is being computed: the dependent plan -> point gather then costs an L2 hit.
-  PairTask t_prev = cnt ? load_task<FIRST>(plan, warp_base + lane + 32u * (size_t)(cnt - 1)) : PairTask{0u, AFF_NONE};
+  auto slot_of2 = [&](size_t t) -> size_t { return perm ? (size_t)perm[t] : t; };
+  size_t p_prev = cnt ? slot_of2(warp_base + lane + 32u * (size_t)(cnt - 1)) : 0;
+  PairTask t_prev = cnt ? load_task<FIRST>(plan, p_prev) : PairTask{0u, AFF_NONE};
 #pragma unroll 1
   for (uint32_t jj = cnt; jj > 0; jj--) {
     const uint32_t j = jj - 1;
-    const size_t p = warp_base + lane + 32u * (size_t)j;
+    const size_t p = p_prev;
     const PairTask t = t_prev;
     if (j > 0) {
-      t_prev = load_task<FIRST>(plan, p - 32u);
+      p_prev = slot_of2(warp_base + lane + 32u * (size_t)(j - 1));
+      t_prev = load_task<FIRST>(plan, p_prev);
       prefetch_point<T, FIRST>(src, t_prev.a);
       if (t_prev.b != AFF_NONE) prefetch_point<T, FIRST>(src, t_prev.b);
       if (j > 1) {

@@ -259,6 +259,12 @@ void ctt_b200_set_input_chunks(int chunks) {
   cfg.tuning.input_chunks = chunks < 0 ? 0 : chunks;
 }
 
+void ctt_b200_set_point_chunks(int pieces) {
+  Config& cfg = config();
+  std::lock_guard<std::mutex> lock(cfg.mu);
+  cfg.tuning.point_chunks = pieces < 0 ? 0 : pieces;
+}
+
 void ctt_b200_set_stream(void* cuda_stream) {
   primary_device();   // the stream belongs to the caller's current device: bind the engine to it now
   Config& cfg = config();

@@ -67,6 +67,7 @@ struct Tuning {
   int affine_levels = -1;     // leading levels of the bucket sums as batched-affine additions: -1 = automatic, 0 = off (XYZZ only)
   int reduce_mode = 0;        // 0 = bit-plane reduction for single MSMs (running-sum chunks for batches), 1 = running-sum chunks always
   int input_chunks = 0;       // host-pointer MSMs: chunks the input crosses PCIe in (0 = automatic, 1 = one piece)
+  int point_chunks = 0;       // host-pointer MSMs: pieces the POINTS arrive in while level 0 of the affine sums starts on the early ones (0 = automatic)
 };
 
 struct Stats {               // filled per call; read back through ctt_b200_last_stats
@@ -157,7 +158,7 @@ struct Engine {
   DeviceBuffer d_scalars, d_points, keys_a, keys_b, vals_a, vals_b, cub_tmp, buckets, part_pts[2], part_keys[2], red_a, red_b, red_planes, bounds;
   // batched-affine levels: run bounds, level offsets, per-level plans, two work arrays (odd / even levels), the prefix-product
   // scratch of the per-thread batch inversions and the survivor list handed to the XYZZ slice kernel
-  DeviceBuffer aff_head, aff_tail, aff_off, aff_blocksum, aff_plan[AFF_MAX_LEVELS], aff_work[2], aff_scratch, keys_s, vals_s;
+  DeviceBuffer aff_head, aff_tail, aff_off, aff_blocksum, aff_plan[AFF_MAX_LEVELS], aff_work[2], aff_scratch, keys_s, vals_s, part_counts, part_starts, part_perm;
   void* h_result = nullptr;   // pinned
   size_t h_result_cap = 0;
   // pinned double buffer through which pageable caller memory is staged (msm_host_on)
@@ -218,6 +219,7 @@ inline Config& config() {
   static Config* c = [] {
     Config* x = new Config;
     if (const char* v = getenv("CTT_B200_INPUT_CHUNKS")) x->tuning.input_chunks = atoi(v);
+    if (const char* v = getenv("CTT_B200_POINT_CHUNKS")) x->tuning.point_chunks = atoi(v);
     if (const char* v = getenv("CTT_B200_REDUCE_MODE")) x->tuning.reduce_mode = atoi(v) == 1 ? 1 : 0;
     if (const char* v = getenv("CTT_B200_AFFINE_LEVELS")) x->tuning.affine_levels = atoi(v);
     if (const char* v = getenv("CTT_B200_FORCE_C")) x->tuning.force_c = atoi(v);
@@ -391,13 +393,21 @@ struct InputChunk {
   cudaEvent_t ready;            // recorded on the copy stream after the chunk's scalars and points (may be null)
 };
 
+// Points of a host call arriving in P pieces (by point index): ready[q] is recorded on the copy stream behind piece q; `stage(q)`, if
+// set, is host work that has to run before that (staging of pageable memory) and records ready[q] itself.
+struct PointChunks {
+  int P = 1;
+  cudaEvent_t* ready = nullptr;
+  const std::function<void(int)>* stage = nullptr;
+};
+
 template <class C>
 host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const void* d_points, size_t n, bool fr_mont,
                                       int force_c, int win_begin, int win_end, cudaEvent_t wait_points = nullptr,
                                       size_t table_stride = 0, size_t batch = 1, bool shared_points = false,
                                       host::HXyzz<typename C::H>* batch_out = nullptr,
                                       const std::vector<InputChunk>* input_chunks = nullptr, void* d_digits_out = nullptr,
-                                      const std::function<void()>* stage_points = nullptr) {
+                                      const PointChunks* point_chunks = nullptr) {
   using T = typename C::T;
   using H = typename C::H;
   using HP = host::HXyzz<H>;
@@ -527,11 +537,16 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
     // points of a host call arrive on the copy stream: nothing up to here reads them, and neither does the batched-affine plan
     // below (run bounds, level offsets, pair lists come from the sorted keys / refs alone), so the wait sits right in front of
     // the first kernel that gathers points
-    // `stage_points` (pageable caller memory): the host-side staging of the points runs HERE in the call sequence, i.e. after digits,
-    // sort and plan have been queued, so the device works on the scalars while the host copies the points
+    // Point pieces of a host call (`point_chunks`): the host-side staging of a piece, if any, runs HERE in the call sequence, i.e. after
+    // digits, sort and plan have been queued, and the engine waits for piece q only in front of the work that needs it.
+    const int PC = (point_chunks && !input_chunks) ? point_chunks->P : 0;
+    auto piece_ready = [&](int q) {
+      if (point_chunks->stage && *point_chunks->stage) (*point_chunks->stage)(q);
+      B200_CUDA_CHECK(cudaStreamWaitEvent(s, point_chunks->ready[q], 0));
+    };
     auto wait_for_points = [&]() {
-      if (stage_points && *stage_points) (*stage_points)();
-      if (!input_chunks && ch.ready) B200_CUDA_CHECK(cudaStreamWaitEvent(s, ch.ready, 0));
+      if (PC) { for (int q = 0; q < PC; q++) piece_ready(q); }
+      else if (!input_chunks && ch.ready) B200_CUDA_CHECK(cudaStreamWaitEvent(s, ch.ready, 0));
     };
     const void* acc_points = pts;
     if (AL) {
@@ -580,11 +595,30 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
       aplan.surv_keys = (uint32_t*)E.keys_s.ptr;
       aplan.surv_vals = (uint32_t*)E.vals_s.ptr;
       k_affine_plan<<<eb, 256, 0, s>>>(keys, vals, entries, no_key, head, tail, off, nb, AL, aplan);
-      wait_for_points();
+      const bool split0 = PC > 1;
+      if (!split0) wait_for_points();
       for (int r = 0; r < AL; r++) {
         const uint32_t* total_ptr = off + (size_t)(r + 1) * off_stride + nb;      // size of level r + 1
         uint32_t* dst = (uint32_t*)E.aff_work[(r + 1) & 1].ptr;
-        if (r == 0)
+        if (r == 0 && split0) {
+          // level 0 by arrival of the point pieces: stable partition of the pair list by the last piece a pair touches, one launch
+          // per piece behind that piece's event (k_part_* in msm_affine.cuh)
+          const uint32_t Pq = (uint32_t)PC;
+          const uint32_t nblk_p = (uint32_t)((level_cap(1) + PART_TILE - 1) / PART_TILE);
+          E.part_counts.ensure((size_t)Pq * nblk_p * 4);
+          E.part_starts.ensure((size_t)(Pq + 1) * 4);
+          E.part_perm.ensure(level_cap(1) * 4);
+          k_part_count<<<nblk_p, PART_THREADS, 0, s>>>((const uint2*)E.aff_plan[0].ptr, total_ptr, (uint32_t)nper, Pq, nblk_p, (uint32_t*)E.part_counts.ptr);
+          k_part_scan<<<1, SCAN_THREADS, 0, s>>>((uint32_t*)E.part_counts.ptr, Pq, nblk_p, (uint32_t*)E.part_starts.ptr);
+          k_part_scatter<<<nblk_p, PART_THREADS, 0, s>>>((const uint2*)E.aff_plan[0].ptr, total_ptr, (uint32_t)nper, Pq, nblk_p,
+                                                          (const uint32_t*)E.part_counts.ptr, (uint32_t*)E.part_perm.ptr);
+          for (int q = 0; q < PC; q++) {
+            piece_ready(q);
+            k_affine_pairs<T, true><<<aff_grid, B200_AFF_THREADS, 0, s>>>(E.aff_plan[0].ptr, total_ptr, (const uint32_t*)pts, dst, (uint4*)E.aff_scratch.ptr,
+                                                                          (const uint32_t*)E.part_perm.ptr, (const uint32_t*)E.part_starts.ptr + q);
+          }
+          launches += 3 + PC - 1;
+        } else if (r == 0)
           k_affine_pairs<T, true><<<aff_grid, B200_AFF_THREADS, 0, s>>>(E.aff_plan[0].ptr, total_ptr, (const uint32_t*)pts, dst, (uint4*)E.aff_scratch.ptr);
         else
           k_affine_pairs<T, false><<<aff_grid, B200_AFF_THREADS, 0, s>>>(E.aff_plan[r].ptr, total_ptr, (const uint32_t*)E.aff_work[r & 1].ptr, dst, (uint4*)E.aff_scratch.ptr);
@@ -912,28 +946,46 @@ host::HXyzz<typename C::H> msm_host_on(int device, const void* coefs, const void
     }
     B200_CUDA_CHECK(cudaEventRecord(t1, E.compute()));
     r = msm_device<C>(E, E.d_scalars.ptr, E.d_points.ptr, len, fr_mont, 0, 0, -1, nullptr, 0, 1, false, nullptr, &chunks);
-  } else if (sbytes + pbytes >= (8u << 20) && (is_pageable_host_memory(coefs) || is_pageable_host_memory(points))) {
-    // pageable caller memory: stage it through the pinned double buffer -- the scalars first; the points only after digits, sort
-    // and the batched-affine plan have been queued (stage_points callback), so that the device is already busy meanwhile
-    host_copy_pool().ensure();
-    E.ensure_stage();
-    int piece = 0;
-    staged_h2d(E, E.d_scalars.ptr, coefs, sbytes, E.copy_stream, piece);
-    B200_CUDA_CHECK(cudaEventRecord(E.ev_chunk[0], E.copy_stream));
-    B200_CUDA_CHECK(cudaStreamWaitEvent(E.compute(), E.ev_chunk[0], 0));
-    B200_CUDA_CHECK(cudaEventRecord(t1, E.compute()));
-    const std::function<void()> stage = [&]() {
-      staged_h2d(E, E.d_points.ptr, points, pbytes, E.copy_stream, piece);
-      B200_CUDA_CHECK(cudaEventRecord(E.ev_points_ready, E.copy_stream));
-    };
-    // the event is recorded inside the callback, before the engine waits on it
-    r = msm_device<C>(E, E.d_scalars.ptr, E.d_points.ptr, len, fr_mont, 0, 0, -1, E.ev_points_ready, 0, 1, false, nullptr, nullptr, nullptr, &stage);
   } else {
-    B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, sbytes, cudaMemcpyHostToDevice, E.compute()));
-    B200_CUDA_CHECK(cudaMemcpyAsync(E.d_points.ptr, points, pbytes, cudaMemcpyHostToDevice, E.copy_stream));
-    B200_CUDA_CHECK(cudaEventRecord(E.ev_points_ready, E.copy_stream));
+    // One piece of scalars, the points in PQ pieces by point index. Pinned caller memory: scalars on the compute stream (digits + sort
+    // need only them), every piece of points queued on the copy stream now with an event behind it. Pageable caller memory (what a C /
+    // Rust / Nim caller passes): staged through the pinned double buffer -- the scalars first, each piece of points only when the
+    // engine asks for it (after digits, sort and plan have been queued; level-0 launches of the earlier pieces already run).
+    int PQ = E.tuning.point_chunks;
+    if (PQ <= 0) PQ = len >= (1u << 19) ? 4 : 1;
+    if (PQ > Engine::MAX_INPUT_CHUNKS) PQ = Engine::MAX_INPUT_CHUNKS;
+    if ((size_t)PQ > len) PQ = 1;
+    const size_t pt = 2 * (size_t)C::COORD_BYTES;
+    // boundaries ceil(len q / PQ): a point index i lies in piece floor(i PQ / len), the classification k_part_* uses
+    auto piece_lo = [&](int q) { return (len * (size_t)q + (size_t)PQ - 1) / (size_t)PQ; };
+    const bool pageable = sbytes + pbytes >= (8u << 20) && (is_pageable_host_memory(coefs) || is_pageable_host_memory(points));
+    PointChunks pc;
+    pc.P = PQ;
+    pc.ready = E.ev_chunk;
+    int piece = 0;
+    std::function<void(int)> stage;
+    if (pageable) {
+      host_copy_pool().ensure();
+      E.ensure_stage();
+      staged_h2d(E, E.d_scalars.ptr, coefs, sbytes, E.copy_stream, piece);
+      B200_CUDA_CHECK(cudaEventRecord(E.ev_points_ready, E.copy_stream));
+      B200_CUDA_CHECK(cudaStreamWaitEvent(E.compute(), E.ev_points_ready, 0));
+      stage = [&](int q) {
+        const size_t lo = piece_lo(q), hi = piece_lo(q + 1);
+        staged_h2d(E, (char*)E.d_points.ptr + lo * pt, (const char*)points + lo * pt, (hi - lo) * pt, E.copy_stream, piece);
+        B200_CUDA_CHECK(cudaEventRecord(E.ev_chunk[q], E.copy_stream));
+      };
+      pc.stage = &stage;
+    } else {
+      B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, sbytes, cudaMemcpyHostToDevice, E.compute()));
+      for (int q = 0; q < PQ; q++) {
+        const size_t lo = piece_lo(q), hi = piece_lo(q + 1);
+        B200_CUDA_CHECK(cudaMemcpyAsync((char*)E.d_points.ptr + lo * pt, (const char*)points + lo * pt, (hi - lo) * pt, cudaMemcpyHostToDevice, E.copy_stream));
+        B200_CUDA_CHECK(cudaEventRecord(E.ev_chunk[q], E.copy_stream));
+      }
+    }
     B200_CUDA_CHECK(cudaEventRecord(t1, E.compute()));
-    r = msm_device<C>(E, E.d_scalars.ptr, E.d_points.ptr, len, fr_mont, 0, 0, -1, E.ev_points_ready);
+    r = msm_device<C>(E, E.d_scalars.ptr, E.d_points.ptr, len, fr_mont, 0, 0, -1, nullptr, 0, 1, false, nullptr, nullptr, nullptr, &pc);
   }
   if (E.collect_timing) cudaEventElapsedTime(&E.stats.ms_h2d, t0, t1);
   if (stats_out) *stats_out = E.stats;

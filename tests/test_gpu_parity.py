@@ -437,6 +437,17 @@ def test_in_process_device_list_closed_form(M, lib, tp):
         M.set_devices([])
     got = M.multi_scalar_mul_vartime_parallel(tp, cv, scal, pts, n)
     assert pyref.jac_bytes_to_affine(got, cv) == want
+    # the same 16 MiB of pageable numpy memory (staged through the pinned double buffer) with the points in 3 and 5 pieces and two
+    # forced affine levels: a piece is staged only when the engine asks for it
+    try:
+        lib.ctt_b200_set_affine_levels(2)
+        for pieces in (3, 5):
+            lib.ctt_b200_set_point_chunks(pieces)
+            got = M.multi_scalar_mul_vartime_parallel(tp, cv, scal, pts, n)
+            assert pyref.jac_bytes_to_affine(got, cv) == want, pieces
+    finally:
+        lib.ctt_b200_set_point_chunks(0)
+        lib.ctt_b200_set_affine_levels(-1)
 
 
 def test_caller_thread_with_another_current_device(M, lib, tp, oracle_lib):
@@ -497,7 +508,17 @@ def test_input_chunks_and_reduce_modes_same_result(M, lib, tp, oracle_lib, curve
                     lib.ctt_b200_set_affine_levels(levels)
                     got = M.multi_scalar_mul_vartime_parallel(tp, cv, cb, pb, n)
                     assert pyref.jac_bytes_to_affine(got, cv) == want, (curve, chunks, mode, levels)
+        # point pieces: level 0 of the affine sums partitioned by the last piece a pair touches (ctt_b200_set_point_chunks)
+        lib.ctt_b200_set_input_chunks(1)
+        lib.ctt_b200_set_reduce_mode(0)
+        for pieces in (2, 3, 4, 7, 8):
+            for levels in (1, 3, 0):
+                lib.ctt_b200_set_point_chunks(pieces)
+                lib.ctt_b200_set_affine_levels(levels)
+                got = M.multi_scalar_mul_vartime_parallel(tp, cv, cb, pb, n)
+                assert pyref.jac_bytes_to_affine(got, cv) == want, (curve, "pieces", pieces, levels)
     finally:
+        lib.ctt_b200_set_point_chunks(0)
         lib.ctt_b200_set_input_chunks(0)
         lib.ctt_b200_set_reduce_mode(0)
         lib.ctt_b200_set_affine_levels(-1)
