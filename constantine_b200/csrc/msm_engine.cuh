@@ -952,7 +952,9 @@ host::HXyzz<typename C::H> msm_host_on(int device, const void* coefs, const void
     // Rust / Nim caller passes): staged through the pinned double buffer -- the scalars first, each piece of points only when the
     // engine asks for it (after digits, sort and plan have been queued; level-0 launches of the earlier pieces already run).
     int PQ = E.tuning.point_chunks;
-    if (PQ <= 0) PQ = len >= (1u << 19) ? 4 : 1;
+    // measured at N = 2^20 (profiles/e2e_point_pieces_r2.jsonl): 1 / 2 / 4 / 8 pieces = 9.38 / 8.49 / 9.42 / 9.50 ms from pinned and
+    // 11.10 / 9.76 / 10.46 / 10.19 ms from pageable memory -- every extra launch of level 0 pays one more inversion per thread
+    if (PQ <= 0) PQ = len >= (1u << 19) ? 2 : 1;
     if (PQ > Engine::MAX_INPUT_CHUNKS) PQ = Engine::MAX_INPUT_CHUNKS;
     if ((size_t)PQ > len) PQ = 1;
     const size_t pt = 2 * (size_t)C::COORD_BYTES;

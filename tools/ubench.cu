@@ -9,6 +9,7 @@
 #include "../constantine_b200/csrc/ec.cuh"
 #include "../constantine_b200/csrc/host_field.hpp"
 #include "field_rr.cuh"
+#include "field_two_pipe.cuh"
 
 using namespace b200;
 
