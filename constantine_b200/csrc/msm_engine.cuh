@@ -979,7 +979,11 @@ host::HXyzz<typename C::H> msm_host_on(int device, const void* coefs, const void
       };
       pc.stage = &stage;
     } else {
-      B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, sbytes, cudaMemcpyHostToDevice, E.compute()));
+      // everything on the copy stream, scalars FIRST: two streams would let the DMA engines reorder the scalars behind a piece of
+      // points (measured: the same binary then takes 10.3 instead of 8.5 ms), and digits / sort / plan are what can start early
+      B200_CUDA_CHECK(cudaMemcpyAsync(E.d_scalars.ptr, coefs, sbytes, cudaMemcpyHostToDevice, E.copy_stream));
+      B200_CUDA_CHECK(cudaEventRecord(E.ev_points_ready, E.copy_stream));
+      B200_CUDA_CHECK(cudaStreamWaitEvent(E.compute(), E.ev_points_ready, 0));
       for (int q = 0; q < PQ; q++) {
         const size_t lo = piece_lo(q), hi = piece_lo(q + 1);
         B200_CUDA_CHECK(cudaMemcpyAsync((char*)E.d_points.ptr + lo * pt, (const char*)points + lo * pt, (hi - lo) * pt, cudaMemcpyHostToDevice, E.copy_stream));
