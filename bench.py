@@ -8,13 +8,15 @@ One "step" = one MSM of 2^logn (scalar, point) pairs (configs[2]: BLS12-381 G1, 
 reduced mod r, points in the prime-order subgroup).  Prints ONE JSON line on rank 0.
 
   value   MSMs/s, inputs resident in HBM when the timed region starts (ctt_b200_msm_device), CUDA events on the stream
-          the kernels are launched on, max over ranks.  N > 1: ONE MSM per step sharded over the ranks by points
-          (strong scaling) + all_gather of the <= N partial points (NCCL) + host combine, inside the timed region.
+          the kernels are launched on, max over ranks.  N > 1: ONE MSM per step, inputs replicated, windows sharded over the ranks
+          (strong scaling): window digits stay on the device, ONE NCCL all_gather + one host pass, inside the timed region.
   e2e     same metric through the reference's own C symbol ctt_bls12_381_g1_jac_multi_scalar_mul_big_coefs_vartime_parallel
-          with HOST (pinned) buffers: H2D of scalars+points and D2H of the window sums inside the timed region.
-  roofline  dominant kernel k_accumulate: algorithmic 32x32->64 integer MACs (3300 per bucket point-add)
-          / its CUDA-event duration, against the measured IMAD.WIDE issue peak (profiles/ubench_r1.jsonl); the HBM
-          fraction (algorithmic bytes / step time vs MEASURED_PEAKS.json) is reported beside it.
+          with HOST (pinned) buffers: H2D of scalars+points and D2H of the window digits inside the timed region; e2e.pageable is
+          the same call with ordinary malloc'd buffers.  Every leg's result is checked against the closed form (closed_form_check).
+  roofline  accumulation phase (batched-affine levels + k_accumulate): algorithmic 32x32->64 integer MACs (3300 per bucket
+          point-add) / its CUDA-event duration, against the measured IMAD.WIDE.X issue peak (profiles/ubench_r1.jsonl,
+          profiles/sass_integer_pipe_r2.txt) -- may exceed 1, see frac_note; frac_executed counts the multiplications really issued.
+          The HBM fraction (algorithmic bytes / step time vs MEASURED_PEAKS.json) is reported beside it.
   cpu_baseline  the oracle's restatement of the reference's CPU algorithm (kind "port": the Nim reference cannot be
           built in this image) on all host cores, bounded sample.
 --impl reference times that same CPU restatement as the reference arm.
@@ -44,9 +46,11 @@ UNIT_FIGURES = {"bls12_381_g1": (3300, 128), "bn254_snarks_g1": (1496, 96), "pal
 # => 148 SMs x 31.65 x 1.965 GHz = 9.2e12 MACs/s.  (A carry-free reduced-radix multiplier was prototyped and is slower:
 # profiles/ubench_r1b.jsonl.)
 INT_MAC_PEAK_PER_S = 9.205e12
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_accumulate launch at N = 2^20, c = 16 from the committed
-# `ncu --set full` capture (profiles/ncu_k_accumulate_r1.txt): 1.413 GB + 0.098 GB.
-NCU_TRAFFIC_BYTES_N20 = 1.511e9
+# dram__bytes_read.sum + dram__bytes_write.sum of the accumulation phase of one MSM at N = 2^20, c = 16 (three k_affine_pairs launches +
+# k_accumulate) from the committed `ncu --set full` capture (profiles/ncu_accumulate_and_reduce_r2.txt): 6.334 GB + 2.224 GB. The
+# algorithmic gather is 1.61 GB: the batched-affine levels trade DRAM traffic (pair lists, two operand reads per pair and pass, prefix
+# products, level results; 24 % of the DRAM peak) for multiplications. Round 1 (XYZZ only, profiles/ncu_k_accumulate_r1.txt): 1.51 GB.
+NCU_TRAFFIC_BYTES_N20 = 8.558e9
 
 
 def workload_string(curve, logn):
@@ -453,8 +457,10 @@ def main():
                                   "sorted entry; batched-affine additions execute ~6 multiplications (+ a shared inversion), so the figure may exceed 1",
                      "frac_executed": executed / (acc_ms * 1e-3) / INT_MAC_PEAK_PER_S, "executed_macs_per_entry": executed / max(1, madds),
                      "traffic": (NCU_TRAFFIC_BYTES_N20 if (world == 1 and args.logn == 20 and st["c"] == 16 and CURVE == "bls12_381_g1") else None),
-                     "traffic_note": "DRAM bytes (read + write) of the phase's launches from the committed ncu --set full captures (profiles/); "
-                                     "algorithmic gather = entries x 96 B = 1.61e9 B",
+                     "traffic_note": "DRAM bytes (read + write) of the phase's four launches from the committed ncu --set full capture "
+                                     "(profiles/ncu_accumulate_and_reduce_r2.txt); algorithmic gather = entries x 96 B = 1.61e9 B -- the affine levels "
+                                     "re-read operands per pass and park prefix products, 24 % of the DRAM peak",
+                     "fmaheavy_pipe_busy_ncu": 0.71,
                      "peak_source": "measured 32x32->64 MAC rate of the register-resident Montgomery multiplier loop (IMAD.WIDE.U32.X carry chains, 2 "
                                     "issue slots each: 31.65 MAC/clk/SM x 148 SM x 1.965 GHz), tools/ubench.cu -> profiles/ubench_r1.jsonl, SASS in profiles/",
                      "algorithmic_work": f"{madds} bucket point-adds x {INT_MACS_PER_POINT_ADD} MACs per step, {acc_ms:.3f} ms"},
