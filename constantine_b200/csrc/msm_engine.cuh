@@ -84,7 +84,8 @@ struct Stats {               // filled per call; read back through ctt_b200_last
 // Window size: minimise  W*N*MADD + W*2^(c-1)*REDUCE  (same shape as the reference's bestBucketBitSize cost,
 // reference ec_multi_scalar_mul_scheduler.nim:172-223, with weights measured on B200, round 2: an accumulated entry costs
 // ~0.32 ns, a bucket of the bit-plane reduction ~1.3 ns on top of a fixed ~0.3 ms; the ratio below reproduces the measured
-// optima c = 13 / 15 / 16 at N = 2^16 / 2^18 / 2^20 for BLS12-381 G1, profiles/sweep_c_r2.jsonl).
+// choices c = 13 / 14 / 16 at N = 2^16 / 2^18 / 2^20 for BLS12-381 G1 (profiles/sweep_c_r2.jsonl, configs_r2.jsonl; c = 15 without affine
+// levels measures 9 % better at 2^18 -- an effect of the slice geometry the model does not carry).
 inline int choose_window(size_t n, int bits, int coord_words = 12) {
   double best = 1e300;
   int best_c = 2;
@@ -135,7 +136,16 @@ struct DeviceBuffer {
     if (bytes <= cap) return;
     if (ptr) B200_CUDA_CHECK(cudaFree(ptr));
     size_t want = bytes + bytes / 8 + 256;
-    B200_CUDA_CHECK(cudaMalloc(&ptr, want));
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) {
+      // the interface has no error channel (reference: void, raises: []; OOM aborts there too): say what was asked for and what is left
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      fprintf(stderr, "[ctt_b200_msm] FATAL: device scratch allocation of %zu MiB failed (%s); %zu MiB free of %zu MiB. Scratch grows with "
+                      "the MSM size (~2 GiB per engine slot at N = 2^20, ~8 GiB at 2^22; ctt_b200_set_concurrency bounds the slots).\n",
+              want >> 20, cudaGetErrorString(e), free_b >> 20, total_b >> 20);
+      abort();
+    }
     cap = want;
   }
   void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
