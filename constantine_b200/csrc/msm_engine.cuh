@@ -681,7 +681,10 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
   if (plane_reduce) {
     const uint32_t Cn = 1u << pr_a, Rn = 1u << pr_rbits;
     // terms summed serially by one lane: as many as keep >= ~8 warps per SM busy, at least 2
-    const size_t want_threads = (size_t)E.sm_count * 256;
+#ifndef B200_REDUCE_THREADS_PER_SM
+#define B200_REDUCE_THREADS_PER_SM 256
+#endif
+    const size_t want_threads = (size_t)E.sm_count * B200_REDUCE_THREADS_PER_SM;
     uint32_t serial = 2;
     while (serial < 64 && nbuckets / (size_t)serial >= want_threads) serial *= 2;
     auto lanes_for = [&](uint32_t len) { uint32_t l = len / serial; if (l < 1) l = 1; if (l > 32) l = 32; return (int)l; };

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--levels", default="0,1,2,3,4")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--cs", default="0", help="forced window sizes to sweep (0 = the engine's choice)")
+    ap.add_argument("--win", default="", help="begin:end -- only this window range (the shard of one rank of a window-sharded multi-GPU run; no result check)")
     a = ap.parse_args()
     import torch
     from constantine_b200 import _lib, msm as M
@@ -42,8 +43,13 @@ def main():
         ok = True
         best = None
         for _ in range(a.reps):
-            got = M.msm_device_ptrs(cv, d_s.data_ptr(), d_pts.data_ptr(), n, force_c=fc)
-            ok = ok and pyref.jac_bytes_to_affine(got, cv) == want
+            if a.win:
+                wb, we = (int(x) for x in a.win.split(":"))
+                M.msm_device_ptrs(cv, d_s.data_ptr(), d_pts.data_ptr(), n, out=M.OUT_XYZZ, force_c=fc or M.plan(cv, n)[0], win_begin=wb, win_end=we)
+                ok = None
+            else:
+                got = M.msm_device_ptrs(cv, d_s.data_ptr(), d_pts.data_ptr(), n, force_c=fc)
+                ok = ok and pyref.jac_bytes_to_affine(got, cv) == want
             st = M.last_stats()
             if best is None or st["ms_total"] < best["ms_total"]:
                 best = st
