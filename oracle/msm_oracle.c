@@ -170,7 +170,8 @@ static void fr_from_mont(uint64_t* out, const uint64_t* in, const field_t* fr) {
 /* ------------------------------------------------------------------ exported API (ctypes) */
 
 /* impl: 0 = naive double-and-add sum, 1 = unsigned-window reference bucket method, 2 = signed-window
- *       one-task-per-window method (the parallel hot path).
+ *       one-task-per-window method (the parallel hot path, Jacobian buckets: the checker), 3 = the same with batched-affine
+ *       bucket sums (the reference's arithmetic for c >= 9; the timed CPU baseline).
  * c:    window size; <= 0 selects the reference's own choice (bestBucketBitSize / parallel dispatch).
  * coefs: n x 4 x u64; canonical BigInt when fr_mont == 0, Fr Montgomery residues when fr_mont != 0
  *        (reference bindings/c_curve_decls_parallel.nim:31-45: big_coefs vs fr_coefs entry points).
@@ -185,7 +186,7 @@ int oracle_msm(const curve_t* cv, void* out, const uint64_t* coefs, const void* 
     for (size_t i = 0; i < n; i++) fr_from_mont(big + 4 * i, coefs + 4 * i, &cv->fr);
     coefs = big;
   }
-  if (c <= 0) c = (impl == 2) ? oracle_parallel_dispatch_c((long)n, bits) : oracle_best_bucket_bit_size((long)n, bits, impl == 2, 1);
+  if (c <= 0) c = (impl >= 2) ? oracle_parallel_dispatch_c((long)n, bits) : oracle_best_bucket_bit_size((long)n, bits, impl >= 2, 1);
   if (c < 2) c = 2;
   if (c > 20) c = 20;
   int rc = c;
@@ -196,7 +197,7 @@ int oracle_msm(const curve_t* cv, void* out, const uint64_t* coefs, const void* 
     if (n == 0) jac_set_inf_##NLV##_##EXTV(r, f);                                                        \
     else if (impl == 0) msm_naive_##NLV##_##EXTV(r, coefs, pts, n, bits, f);                             \
     else if (impl == 1) msm_reference_##NLV##_##EXTV(r, coefs, pts, n, c, bits, f);                      \
-    else msm_signed_##NLV##_##EXTV(r, coefs, pts, n, c, bits, f, nthreads);                              \
+    else msm_signed_##NLV##_##EXTV(r, coefs, pts, n, c, bits, f, nthreads, impl == 3);                   \
   } while (0)
   if (f->nl == 4 && cv->ext == 1) DISPATCH(4, 1);
   else if (f->nl == 4 && cv->ext == 2) DISPATCH(4, 2);

@@ -331,13 +331,193 @@ static void FN(window_signed)(jac_t* window_sum, int kind, int bit_index, int c,
   free(buckets);
 }
 
+/* ------------------------------------------------------------------ batched-affine bucket sums (TIMED path of the CPU arm)
+ * The reference accumulates buckets for c >= 9 with affine additions that share one inversion per batch
+ * (ec_multi_scalar_mul_scheduler.nim:414-553 sparseVectorAddition, ec_shortweierstrass_batch_ops.nim:424-455 affineAdd:
+ * 6 field multiplications per addition + the amortised inversion, instead of 11 for a Jacobian mixed addition). The reference
+ * feeds those batches from a collision-avoiding scheduler; this restatement gets collision-free batches the way the GPU
+ * engine does -- counting sort of the window's digits, then pairwise tree sums per bucket, level by level -- which performs
+ * the same additions (same formulas, same special cases) and yields the same group element. It exists so that the CPU baseline
+ * bench.py reports is not handicapped by Jacobian buckets; the plain path above stays the checker. */
+
+/* a^(p-2): Fermat inversion, once per batch of up to AFF_BATCH additions */
+static void FN(fp_inv)(fp_t* r, const fp_t* a, const field_t* f) {
+  uint64_t e[NL];
+  for (int i = 0; i < NL; i++) e[i] = f->p[i];
+  e[0] -= 2;   /* p is odd and > 2 */
+  fp_t acc, b = *a;
+  for (int i = 0; i < NL; i++) acc.l[i] = f->one[i];
+  for (int i = 0; i < 64 * NL; i++) {
+    if ((e[i >> 6] >> (i & 63)) & 1) FN(fp_mul)(&acc, &acc, &b, f);
+    FN(fp_mul)(&b, &b, &b, f);
+  }
+  *r = acc;
+}
+static void FN(fe_inv)(fe_t* r, const fe_t* a, const field_t* f) {
+#if EXT == 1
+  FN(fp_inv)(&r->c[0], &a->c[0], f);
+#else
+  /* 1 / (a0 + a1 i) = (a0 - a1 i) / (a0^2 + a1^2)   (reference extension_fields/towers.nim, inv of a quadratic extension) */
+  fp_t n0, n1, n;
+  FN(fp_mul)(&n0, &a->c[0], &a->c[0], f);
+  FN(fp_mul)(&n1, &a->c[1], &a->c[1], f);
+  FN(fp_add)(&n, &n0, &n1, f);
+  FN(fp_inv)(&n, &n, f);
+  FN(fp_mul)(&r->c[0], &a->c[0], &n, f);
+  FN(fp_mul)(&n1, &a->c[1], &n, f);
+  FN(fp_neg)(&r->c[1], &n1, f);
+#endif
+}
+
+#define AFF_BATCH 1024
+
+/* out[i] = a[i] + b[i] for i < m (m <= AFF_BATCH) with one shared inversion.
+ * kind: 0 add (lambda = (y2 - y1) / (x2 - x1)), 1 double (lambda = 3 x^2 / 2y), 2 result = a, 3 result = b, 4 infinity
+ * (reference lambdaAdd / lambdaDouble / the special cases of sparseVectorAddition, scheduler.nim:465-479, 513-516) */
+static void FN(affine_add_batch)(aff_t* out, const aff_t* a, const aff_t* b, int m, const field_t* f) {
+  fe_t den[AFF_BATCH], pre[AFF_BATCH];
+  unsigned char kind[AFF_BATCH];
+  fe_t run;
+  FN(fe_set_one)(&run, f);
+  for (int i = 0; i < m; i++) {
+    if (FN(aff_is_inf)(&a[i])) kind[i] = 3;
+    else if (FN(aff_is_inf)(&b[i])) kind[i] = 2;
+    else {
+      FN(fe_sub)(&den[i], &b[i].x, &a[i].x, f);
+      if (!FN(fe_is_zero)(&den[i])) kind[i] = 0;
+      else if (FN(fe_eq)(&a[i].y, &b[i].y) && !FN(fe_is_zero)(&a[i].y)) { kind[i] = 1; FN(fe_add)(&den[i], &a[i].y, &a[i].y, f); }
+      else kind[i] = 4;
+    }
+    if (kind[i] <= 1) FN(fe_mul)(&run, &run, &den[i], f);
+    pre[i] = run;
+  }
+  fe_t inv;
+  FN(fe_inv)(&inv, &run, f);
+  for (int i = m - 1; i >= 0; i--) {
+    if (kind[i] == 2) { out[i] = a[i]; continue; }
+    if (kind[i] == 3) { out[i] = b[i]; continue; }
+    if (kind[i] == 4) { memset(&out[i], 0, sizeof(aff_t)); continue; }
+    fe_t inv_den, num, lam, t;
+    /* 1 / den_i = inv * (product of the earlier denominators) */
+    int j = i - 1;
+    while (j >= 0 && kind[j] > 1) j--;
+    if (j >= 0) FN(fe_mul)(&inv_den, &inv, &pre[j], f); else inv_den = inv;
+    FN(fe_mul)(&inv, &inv, &den[i], f);
+    if (kind[i] == 0) FN(fe_sub)(&num, &b[i].y, &a[i].y, f);
+    else { FN(fe_sqr)(&t, &a[i].x, f); FN(fe_add)(&num, &t, &t, f); FN(fe_add)(&num, &num, &t, f); }   /* 3 x^2 (a = 0) */
+    FN(fe_mul)(&lam, &num, &inv_den, f);
+    aff_t r;
+    FN(fe_sqr)(&t, &lam, f);
+    FN(fe_sub)(&t, &t, &a[i].x, f);
+    FN(fe_sub)(&r.x, &t, &b[i].x, f);
+    FN(fe_sub)(&t, &a[i].x, &r.x, f);
+    FN(fe_mul)(&t, &lam, &t, f);
+    FN(fe_sub)(&r.y, &t, &a[i].y, f);
+    out[i] = r;
+  }
+}
+
+/* One window with batched-affine bucket sums: counting sort by bucket, pairwise levels, then the same running-sum reduction
+ * (the bucket enters it as an affine point: Jacobian mixed addition for accum += bucket). */
+static void FN(window_signed_affine)(jac_t* window_sum, int kind, int bit_index, int c, int bits,
+                                     const uint64_t* coefs, const aff_t* points, size_t n, const field_t* f) {
+  size_t nb = (size_t)1 << (c - 1);
+  int excess = bits % c, top = bits - excess;
+  uint32_t* cnt = (uint32_t*)calloc(nb + 1, sizeof(uint32_t));
+  uint32_t* dig = (uint32_t*)malloc(n * sizeof(uint32_t));          /* bucket + 1 (0 = none) | sign << 31 */
+  for (size_t j = 0; j < n; j++) {
+    uint64_t val; int neg;
+    const uint64_t* k = coefs + j * SCALAR_LIMBS;
+    if (kind == 0) signed_bottom_window(k, c, &val, &neg);
+    else if (kind == 2) signed_top_window(k, top, excess, &val, &neg);
+    else signed_full_window(k, bit_index, c, &val, &neg);
+    if (val && FN(aff_is_inf)(&points[j])) val = 0;                  /* a point at infinity contributes nothing */
+    dig[j] = (uint32_t)val | ((uint32_t)neg << 31);
+    if (val) cnt[val - 1]++;
+  }
+  /* counting sort of the point REFERENCES (index | sign << 31) by bucket; level 0 gathers the points through them */
+  uint32_t* off = (uint32_t*)malloc((nb + 1) * sizeof(uint32_t));
+  uint32_t tot = 0;
+  for (size_t b = 0; b < nb; b++) { off[b] = tot; tot += cnt[b]; }
+  off[nb] = tot;
+  uint32_t* ord = (uint32_t*)malloc(((size_t)tot + 1) * sizeof(uint32_t));
+  uint32_t* fill = (uint32_t*)malloc(nb * sizeof(uint32_t));
+  memcpy(fill, off, nb * sizeof(uint32_t));
+  for (size_t j = 0; j < n; j++) {
+    uint32_t v = dig[j] & 0x7FFFFFFFu;
+    if (!v) continue;
+    ord[fill[v - 1]++] = (uint32_t)j | (dig[j] & 0x80000000u);
+  }
+  free(dig); free(fill);
+  aff_t* cur = (aff_t*)malloc(((size_t)tot / 2 + nb + 1) * sizeof(aff_t));
+  aff_t* nxt = (aff_t*)malloc(((size_t)tot / 4 + nb + 1) * sizeof(aff_t));
+#define ORD_POINT(dst, k) do { uint32_t o_ = ord[k]; (dst) = points[o_ & 0x7FFFFFFFu]; \
+                               if (o_ >> 31) FN(fe_neg)(&(dst).y, &points[o_ & 0x7FFFFFFFu].y, f); } while (0)
+  /* levels */
+  aff_t *ba = (aff_t*)malloc(AFF_BATCH * sizeof(aff_t)), *bb = (aff_t*)malloc(AFF_BATCH * sizeof(aff_t)), *bo = (aff_t*)malloc(AFF_BATCH * sizeof(aff_t));
+  uint32_t* dst_idx = (uint32_t*)malloc(AFF_BATCH * sizeof(uint32_t));
+  int first = 1;
+  for (;;) {
+    uint32_t maxc = 0;
+    for (size_t b = 0; b < nb; b++) if (cnt[b] > maxc) maxc = cnt[b];
+    if (maxc <= 1 && !first) break;
+    aff_t* dst = first ? cur : nxt;   /* level 0 reads through `ord` and writes cur; later levels read cur and write nxt */
+    uint32_t w = 0;         /* write position */
+    int m = 0;
+    uint32_t r = 0;         /* read position */
+    for (size_t b = 0; b < nb; b++) {
+      uint32_t cb = cnt[b];
+      uint32_t pairs = cb / 2;
+      for (uint32_t i = 0; i < pairs; i++) {
+        if (first) { ORD_POINT(ba[m], r + 2 * i); ORD_POINT(bb[m], r + 2 * i + 1); }
+        else { ba[m] = cur[r + 2 * i]; bb[m] = cur[r + 2 * i + 1]; }
+        dst_idx[m] = w + i; m++;
+        if (m == AFF_BATCH) {
+          FN(affine_add_batch)(bo, ba, bb, m, f);
+          for (int q = 0; q < m; q++) dst[dst_idx[q]] = bo[q];
+          m = 0;
+        }
+      }
+      if (cb & 1) { if (first) ORD_POINT(dst[w + pairs], r + cb - 1); else dst[w + pairs] = cur[r + cb - 1]; }
+      r += cb;
+      cnt[b] = pairs + (cb & 1);
+      w += cnt[b];
+    }
+    if (m) {
+      FN(affine_add_batch)(bo, ba, bb, m, f);
+      for (int q = 0; q < m; q++) dst[dst_idx[q]] = bo[q];
+    }
+    if (first) first = 0;
+    else { aff_t* t = cur; cur = nxt; nxt = t; }
+  }
+#undef ORD_POINT
+  free(ord);
+  free(ba); free(bb); free(bo); free(dst_idx);
+  /* running-sum reduction over the (affine or empty) buckets  (reference ec_multi_scalar_mul.nim:186-197) */
+  jac_t accum, res;
+  FN(jac_set_inf)(&accum, f);
+  FN(jac_set_inf)(&res, f);
+  {
+    /* cur holds the surviving points in bucket order: walk it backwards together with the counts */
+    uint32_t pos = 0;
+    for (size_t b = 0; b < nb; b++) pos += cnt[b];
+    for (size_t k = nb; k-- > 0;) {
+      if (cnt[k]) { pos--; FN(jac_madd)(&accum, &accum, &cur[pos], f); }
+      FN(jac_add)(&res, &res, &accum, f);
+    }
+  }
+  *window_sum = res;
+  free(cnt); free(off); free(cur); free(nxt);
+}
+
 typedef struct {
-  jac_t* out; int kind, bit_index, c, bits; const uint64_t* coefs; const aff_t* points; size_t n; const field_t* f;
+  jac_t* out; int kind, bit_index, c, bits; const uint64_t* coefs; const aff_t* points; size_t n; const field_t* f; int affine;
 } FN(wtask);
 
 static void FN(run_wtask)(void* arg) {
   FN(wtask)* t = (FN(wtask)*)arg;
-  FN(window_signed)(t->out, t->kind, t->bit_index, t->c, t->bits, t->coefs, t->points, t->n, t->f);
+  if (t->affine) FN(window_signed_affine)(t->out, t->kind, t->bit_index, t->c, t->bits, t->coefs, t->points, t->n, t->f);
+  else FN(window_signed)(t->out, t->kind, t->bit_index, t->c, t->bits, t->coefs, t->points, t->n, t->f);
 }
 
 /* Signed-window bucket MSM, one task per (sub-MSM, window) -- the structure of
@@ -350,7 +530,7 @@ static void FN(run_wtask)(void* arg) {
  * For c >= 9 the reference swaps Jacobian buckets for the batched-affine scheduler (:316-384) -- a CPU cache
  * optimisation that yields the same group element and is not restated. */
 static void FN(msm_signed)(jac_t* r, const uint64_t* coefs, const aff_t* points, size_t n, int c, int bits,
-                           const field_t* f, int nthreads) {
+                           const field_t* f, int nthreads, int affine) {
   int num_full = bits / c;
   int excess = bits % c, top = bits - excess;
   int nwin = num_full + 1;
@@ -366,7 +546,7 @@ static void FN(msm_signed)(jac_t* r, const uint64_t* coefs, const aff_t* points,
       int kind = (w == 0) ? 0 : 1;
       int bit_index = w * c;
       if (w == num_full) { kind = (top == 0) ? 0 : (excess == 0 ? 1 : 2); bit_index = top; }
-      FN(wtask) t = { &sums[ch * nwin + w], kind, bit_index, c, bits, coefs + start * SCALAR_LIMBS, points + start, len, f };
+      FN(wtask) t = { &sums[ch * nwin + w], kind, bit_index, c, bits, coefs + start * SCALAR_LIMBS, points + start, len, f, affine };
       tasks[ch * nwin + w] = t;
     }
   }

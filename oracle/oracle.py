@@ -68,7 +68,7 @@ def load():
     return _lib
 
 
-IMPL_NAIVE, IMPL_REFERENCE, IMPL_SIGNED = 0, 1, 2
+IMPL_NAIVE, IMPL_REFERENCE, IMPL_SIGNED, IMPL_SIGNED_AFFINE = 0, 1, 2, 3
 
 
 def msm(curve: CurveParams, coefs: bytes, points: bytes, n: int, fr_mont=False, impl=IMPL_SIGNED, c=0, nthreads=0) -> bytes:

@@ -6,7 +6,7 @@ import pytest
 from helpers import CURVES, case_inputs, pack, pyref
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
 def test_oracle_eip2537_vectors(kat, oracle_lib, impl):
     """reference tests/protocol_ethereum_evm_precompiles/eip-2537/multiexp_G{1,2}_bls.json -- byte-pinned MSM results."""
     assert len(kat["eip2537"]) == 27
@@ -17,7 +17,7 @@ def test_oracle_eip2537_vectors(kat, oracle_lib, impl):
         assert got == want, case["name"]
 
 
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 2, 3])
 def test_oracle_sage_vector_sums(kat, oracle_lib, impl):
     """reference tests/math_elliptic_curves/vectors/tv_*_scalar_mul_*.json: each file as one 40-term MSM."""
     assert len(kat["sage_scalar_mul"]) == 18

@@ -71,3 +71,25 @@ def test_threads_do_not_change_the_result(oracle_lib, rng):
     a = oracle_lib.msm(cv, cb, pb, n, nthreads=1)
     b = oracle_lib.msm(cv, cb, pb, n, nthreads=8)
     assert a == b
+
+
+def test_batched_affine_cpu_path_equals_the_checker(oracle_lib, rng):
+    """impl 3 (the TIMED CPU baseline: signed windows + sort-based batched-affine bucket sums, the reference's arithmetic for
+    c >= 9) returns the same group element as impl 2 (Jacobian buckets, the checker) on every group -- few distinct points so that
+    P + P and P - P land inside the batches, an infinity input, a zero scalar, N = 1 and 2, several window sizes."""
+    for curve, n in (("bls12_381_g1", 3000), ("bn254_snarks_g1", 777), ("bls12_381_g2", 300), ("pallas_ec", 50), ("vesta_ec", 1),
+                     ("bn254_snarks_g2", 2)):
+        cv = CURVES[curve]
+        _, pool = point_pool(cv)
+        pts = [pool[rng.randrange(6)] for _ in range(n)]
+        ks = [rng.getrandbits(cv.scalar_bits) for _ in range(n)]
+        if n > 10:
+            pts[3] = None
+            ks[5] = 0
+            ks[6] = ks[7]
+            pts[6] = pts[7]
+        cb, pb = pack(cv, ks, pts)
+        want = pyref.jac_bytes_to_affine(oracle_lib.msm(cv, cb, pb, n), cv)
+        for c in (0, 2, 4, 9, 13):
+            got = pyref.jac_bytes_to_affine(oracle_lib.msm(cv, cb, pb, n, impl=oracle_lib.IMPL_SIGNED_AFFINE, c=c), cv)
+            assert got == want, (curve, c)
