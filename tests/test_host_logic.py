@@ -164,3 +164,21 @@ def test_bit_plane_bucket_reduction_identity():
         for e in range(emax, -1, -1):
             r = 2 * r + by_exp[e]
         assert r == want
+
+
+def test_point_piece_boundaries_match_the_pair_classification():
+    """msm_engine.cuh msm_host_on cuts the points into P pieces at ceil(n q / P); msm_affine.cuh pair_chunk classifies a point index i
+    as floor(i P / n). A pair may only be scheduled with the pieces of both operands present, so the two must agree for every
+    index -- in particular never classify an index EARLIER than the piece that carries it."""
+    import random
+    rnd = random.Random(11)
+    for _ in range(300):
+        n = rnd.choice([1, 2, 3, 7, 64, 1000, 4097, 65536, 70001, (1 << 20) + 5, rnd.randrange(1, 1 << 22)])
+        for P in range(1, 9):
+            if P > n:
+                continue
+            lo = [(n * q + P - 1) // P for q in range(P + 1)]
+            assert lo[0] == 0 and lo[P] == n and all(a <= b for a, b in zip(lo, lo[1:]))
+            for i in {0, n - 1, n // 2, *(min(n - 1, x) for x in lo[:-1]), *(max(0, x - 1) for x in lo[1:]), rnd.randrange(n)}:
+                q = min(P - 1, i * P // n)
+                assert lo[q] <= i < lo[q + 1], (n, P, i, q)
