@@ -203,8 +203,8 @@ def time_oracle(n_full, budget_s=20.0, max_logn=20):
     return {"value": 1.0 / (t * scale), "unit": "MSM/s", "cores": cores, "kind": "port",
             "sample": f"one MSM of 2^{logn} pairs in {t:.2f} s (c={c}, {padds / t / 1e6:.1f} Mop point-adds/s = "
                       f"{padds / t / 1e6 / cores:.2f} per thread), scaled x{scale:g} to N=2^{n_full.bit_length() - 1}; "
-                      "portable C port with batched-affine bucket sums, NOT Constantine: the reference publishes 33 Mop/s on 16 Zen4 threads "
-                      "at N=2^18 (BASELINE.md) with ADX assembly",
+                      "C port with batched-affine bucket sums and a MULX/ADX multiplication, NOT Constantine itself: the reference "
+                      "publishes 33 Mop/s on 16 Zen4 threads at N=2^18 (BASELINE.md)",
             "point_adds_per_s": padds / t, "seconds": t, "logn": logn}
 
 
@@ -225,8 +225,9 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload_string(CURVE, args.logn), "note":
-                       "portable C restatement (oracle port, NOT Constantine itself: batched-affine bucket sums like the reference, but "
-                       "no ADX/MULX assembly) of the reference's parallel MSM on all host cores; the Nim reference cannot be built in this image"},
+                       "C restatement (oracle port, NOT Constantine itself) of the reference's parallel MSM on all host cores: its window "
+                       "choice, MSM-level split, batched-affine bucket sums and a MULX/ADX Montgomery multiplication; the Nim reference "
+                       "cannot be built in this image"},
             "cpu_baseline": {"value": v, "unit": "MSM/s", "cores": info["cores"], "kind": "port", "sample": info["sample"]},
             "e2e": {"value": v, "unit": "MSM/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))

@@ -23,6 +23,14 @@
 
 typedef unsigned __int128 u128;
 
+/* MULX / ADCX / ADOX multiplication for the TIMED CPU baseline (impl 3): compiled in on x86-64, switched on at run time only when
+ * the CPU has BMI2 + ADX (the library is built in the dev container and travels to the GPU box) and only for impl 3, so that the
+ * checker paths stay on the portable multiplication. */
+#if defined(__x86_64__) && defined(__GNUC__)
+#define ORACLE_HAVE_MULX_ADX 1
+#endif
+static int g_fast_mul = 0;
+
 #define SCALAR_LIMBS 4 /* every scalar field on this path is 254/255 bits = 4 x u64 (reference curves/bigints.h:18-21) */
 
 typedef struct {
@@ -190,6 +198,9 @@ int oracle_msm(const curve_t* cv, void* out, const uint64_t* coefs, const void* 
   if (c < 2) c = 2;
   if (c > 20) c = 20;
   int rc = c;
+#if defined(ORACLE_HAVE_MULX_ADX)
+  g_fast_mul = (impl == 3) && __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("adx");
+#endif
 #define DISPATCH(NLV, EXTV)                                                                              \
   do {                                                                                                   \
     jac_##NLV##_##EXTV* r = (jac_##NLV##_##EXTV*)out;                                                    \
@@ -205,6 +216,7 @@ int oracle_msm(const curve_t* cv, void* out, const uint64_t* coefs, const void* 
   else if (f->nl == 6 && cv->ext == 2) DISPATCH(6, 2);
   else rc = -1;
 #undef DISPATCH
+  g_fast_mul = 0;
   free(big);
   return rc;
 }

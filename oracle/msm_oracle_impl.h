@@ -87,10 +87,72 @@ static inline void FN(fp_div2)(fp_t* r, const fp_t* a, const field_t* f) {
   t[NL] = (uint64_t)c;
   for (int i = 0; i < NL; i++) r->l[i] = (t[i] >> 1) | (t[i + 1] << 63);
 }
+#if defined(ORACLE_HAVE_MULX_ADX)
+/* The same CIOS multiplication on MULX + the two ADCX / ADOX carry chains -- what the reference's x86 path does in assembly
+ * (constantine/math/arithmetic/assembly/limbs_asm_mul_mont_x86_adx_bmi2.nim). One row: t[0..NL] += x[0..NL-1] * y, carries into t[NL+1].
+ * Used only by the TIMED CPU baseline (g_fast_mul); validated against the portable multiplication in tests/test_oracle_vs_exact.py. */
+#if NL == 6
+#define ORACLE_ROW(t0, t1, t2, t3, t4, t5, t6, t7, xp, y)                                                      \
+  __asm__ volatile(                                                                                            \
+      "xorl %%eax, %%eax\n\t"                                                                                  \
+      "mulx 0(%[x]), %%r8, %%r9\n\t" "adox %%r8, %[a0]\n\t" "adcx %%r9, %[a1]\n\t"                           \
+      "mulx 8(%[x]), %%r8, %%r9\n\t" "adox %%r8, %[a1]\n\t" "adcx %%r9, %[a2]\n\t"                           \
+      "mulx 16(%[x]), %%r8, %%r9\n\t" "adox %%r8, %[a2]\n\t" "adcx %%r9, %[a3]\n\t"                          \
+      "mulx 24(%[x]), %%r8, %%r9\n\t" "adox %%r8, %[a3]\n\t" "adcx %%r9, %[a4]\n\t"                          \
+      "mulx 32(%[x]), %%r8, %%r9\n\t" "adox %%r8, %[a4]\n\t" "adcx %%r9, %[a5]\n\t"                          \
+      "mulx 40(%[x]), %%r8, %%r9\n\t" "adox %%r8, %[a5]\n\t" "adcx %%r9, %[a6]\n\t"                          \
+      "movl $0, %%r8d\n\t" "adox %%r8, %[a6]\n\t" "adcx %%r8, %[a7]\n\t" "adox %%r8, %[a7]\n\t"              \
+      : [a0] "+r"(t0), [a1] "+r"(t1), [a2] "+r"(t2), [a3] "+r"(t3), [a4] "+r"(t4), [a5] "+r"(t5), [a6] "+r"(t6), [a7] "+r"(t7) \
+      : [x] "r"(xp), "d"(y)                                                                                    \
+      : "rax", "r8", "r9", "cc", "memory")
+static inline void FN(fp_mul_mulx_adx)(fp_t* r, const fp_t* a, const fp_t* b, const field_t* f) {
+  uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0, t7 = 0;
+  for (int i = 0; i < 6; i++) {
+    ORACLE_ROW(t0, t1, t2, t3, t4, t5, t6, t7, a->l, b->l[i]);
+    const uint64_t m = t0 * f->m0ninv;
+    ORACLE_ROW(t0, t1, t2, t3, t4, t5, t6, t7, f->p, m);
+    t0 = t1; t1 = t2; t2 = t3; t3 = t4; t4 = t5; t5 = t6; t6 = t7; t7 = 0;
+  }
+  fp_t o = {{t0, t1, t2, t3, t4, t5}};
+  if (t6 || FN(fp_geq_p)(&o, f)) FN(fp_sub_p)(&o, f);
+  *r = o;
+}
+#undef ORACLE_ROW
+#else
+#define ORACLE_ROW(t0, t1, t2, t3, t4, t5, xp, y)                                                              \
+  __asm__ volatile(                                                                                            \
+      "xorl %%eax, %%eax\n\t"                                                                                  \
+      "mulx 0(%[x]), %%r8, %%r9\n\t" "adox %%r8, %[a0]\n\t" "adcx %%r9, %[a1]\n\t"                           \
+      "mulx 8(%[x]), %%r8, %%r9\n\t" "adox %%r8, %[a1]\n\t" "adcx %%r9, %[a2]\n\t"                           \
+      "mulx 16(%[x]), %%r8, %%r9\n\t" "adox %%r8, %[a2]\n\t" "adcx %%r9, %[a3]\n\t"                          \
+      "mulx 24(%[x]), %%r8, %%r9\n\t" "adox %%r8, %[a3]\n\t" "adcx %%r9, %[a4]\n\t"                          \
+      "movl $0, %%r8d\n\t" "adox %%r8, %[a4]\n\t" "adcx %%r8, %[a5]\n\t" "adox %%r8, %[a5]\n\t"              \
+      : [a0] "+r"(t0), [a1] "+r"(t1), [a2] "+r"(t2), [a3] "+r"(t3), [a4] "+r"(t4), [a5] "+r"(t5)               \
+      : [x] "r"(xp), "d"(y)                                                                                    \
+      : "rax", "r8", "r9", "cc", "memory")
+static inline void FN(fp_mul_mulx_adx)(fp_t* r, const fp_t* a, const fp_t* b, const field_t* f) {
+  uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
+  for (int i = 0; i < 4; i++) {
+    ORACLE_ROW(t0, t1, t2, t3, t4, t5, a->l, b->l[i]);
+    const uint64_t m = t0 * f->m0ninv;
+    ORACLE_ROW(t0, t1, t2, t3, t4, t5, f->p, m);
+    t0 = t1; t1 = t2; t2 = t3; t3 = t4; t4 = t5; t5 = 0;
+  }
+  fp_t o = {{t0, t1, t2, t3}};
+  if (t4 || FN(fp_geq_p)(&o, f)) FN(fp_sub_p)(&o, f);
+  *r = o;
+}
+#undef ORACLE_ROW
+#endif
+#endif /* ORACLE_HAVE_MULX_ADX */
+
 /* reference limbs_montgomery.nim:180-217 (mulMont_CIOS_sparebit): coarsely integrated operand scanning,
  * one interleaved reduction per limb of b; final conditional subtraction (finite_fields.nim:268-281 keeps
  * values canonical unless lazyReduce is requested -- the oracle never uses lazyReduce). */
 static inline void FN(fp_mul)(fp_t* r, const fp_t* a, const fp_t* b, const field_t* f) {
+#if defined(ORACLE_HAVE_MULX_ADX)
+  if (g_fast_mul) { FN(fp_mul_mulx_adx)(r, a, b, f); return; }   /* timed CPU arm only (oracle_msm impl 3); the checker stays portable */
+#endif
   uint64_t t[NL + 2];
   for (int i = 0; i < NL + 2; i++) t[i] = 0;
   for (int i = 0; i < NL; i++) {
