@@ -495,7 +495,11 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
     {
       double mean_run = (double)acc_entries / (double)nbuckets;
       while (KACC < 256 && KACC < 2.0 * mean_run && acc_entries / (size_t)(2 * KACC) >= (size_t)4 * 148 * 256) KACC *= 2;
-      if (acc_entries / 32 < (size_t)2 * 148 * 256) KACC = 16;   // fewer than two waves of slices: halve them so the SMs fill evenly
+      // fewer than two waves of slices (N <= 2^16, or the window shard of one rank of a multi-GPU run). Short runs: halve the
+      // slices so the SMs fill evenly. Long runs (>= 24 entries per bucket): the walk is latency-bound either way and its time
+      // does not move with the slice length, but every slice boundary inside a run is a partial sum k_fixup has to fold --
+      // K = 64 cuts that from 0.26 to 0.05 ms on a 2-window shard of N = 2^20 (profiles/slice_sweep_r2q.txt)
+      if (acc_entries / 32 < (size_t)2 * 148 * 256) KACC = mean_run >= 24.0 ? 64 : 16;
       if (E.tuning.slice_len > 0) KACC = E.tuning.slice_len;
     }
     st.slice_len = KACC;
