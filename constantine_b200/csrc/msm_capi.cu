@@ -232,7 +232,8 @@ void ctt_b200_set_tuning(int force_c, int reduce_chunk, int slice_len) {
   if (force_c < 0) cfg.tuning.force_c = 0;
   if (reduce_chunk > 0) cfg.tuning.reduce_chunk = reduce_chunk;
   if (slice_len > 0) cfg.tuning.slice_len = slice_len;
-  if (slice_len < 0) cfg.tuning.slice_len = 0;
+  if (slice_len == -1) cfg.tuning.slice_len = 0;
+  if (slice_len < -1) cfg.tuning.slice_len = slice_len;   // automatic, with |slice_len| as the upper limit
 }
 
 void ctt_b200_set_groups(int groups) {

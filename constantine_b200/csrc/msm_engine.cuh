@@ -489,20 +489,26 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
     // level r holds sum_b ceil(n_b / 2^r) <= entries / 2^r + nbuckets slots
     auto level_cap = [&](int r) { return (entries >> r) + nbuckets + 1; };
     const size_t acc_entries = AL ? level_cap(AL) : entries;   // upper bound of the list k_accumulate walks
-    // slice length: about twice the mean run length (entries per bucket) so that few slices sit entirely inside one run, but
-    // never so long that the grid cannot fill the machine
-    int KACC = 32;
+    // slice length of k_accumulate. Every thread of a resident wave walks one slice, so the kernel's time is (waves) x (slice
+    // length) whatever the fill of the last wave: the slices are sized to fill a whole number of waves, on the device, from the
+    // actual entry count (accumulate_slice_len in msm_kernels.cuh; measured on the shapes of profiles/slice_sweep_r2q.txt,
+    // where fixed lengths 16 / 32 / 64 differ by exactly their wave counts). KACC is the upper limit: longer slices mean fewer
+    // partial sums for k_fixup but coarser balance. tuning.slice_len > 0 fixes the length instead (sweeps), < 0 sets the limit.
+    int KACC = 64;
+    uint32_t fit_threads;
     {
-      double mean_run = (double)acc_entries / (double)nbuckets;
-      while (KACC < 256 && KACC < 2.0 * mean_run && acc_entries / (size_t)(2 * KACC) >= (size_t)4 * 148 * 256) KACC *= 2;
-      // fewer than two waves of slices (N <= 2^16, or the window shard of one rank of a multi-GPU run). Short runs: halve the
-      // slices so the SMs fill evenly. Long runs (>= 24 entries per bucket): the walk is latency-bound either way and its time
-      // does not move with the slice length, but every slice boundary inside a run is a partial sum k_fixup has to fold --
-      // K = 64 cuts that from 0.26 to 0.05 ms on a 2-window shard of N = 2^20 (profiles/slice_sweep_r2q.txt)
-      if (acc_entries / 32 < (size_t)2 * 148 * 256) KACC = mean_run >= 24.0 ? 64 : 16;
-      if (E.tuning.slice_len > 0) KACC = E.tuning.slice_len;
+      static thread_local int acc_bps_cache[MAX_DEVICES] = {};
+      int bps = acc_bps_cache[E.device];
+      if (bps == 0) {
+        B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_accumulate<T>, B200_ACC_THREADS, 0));
+        if (bps < 1) bps = 1;
+        acc_bps_cache[E.device] = bps;
+      }
+      fit_threads = (uint32_t)(E.sm_count * bps * B200_ACC_THREADS);
+      if (E.tuning.slice_len > 0) { KACC = E.tuning.slice_len; fit_threads = 0; }
+      else if (E.tuning.slice_len < 0) KACC = -E.tuning.slice_len;
     }
-    st.slice_len = KACC;
+    st.slice_len = fit_threads ? accumulate_slice_len(acc_entries, fit_threads, KACC) : KACC;   // (fitted: for the upper bound of the list)
     E.keys_a.ensure(entries * 4); E.keys_b.ensure(entries * 4);
     E.vals_a.ensure(entries * 4); E.vals_b.ensure(entries * 4);
     if (timed) B200_CUDA_CHECK(cudaEventRecord(E.ev[10], s));
@@ -543,7 +549,8 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
     {
       size_t set_cap = table_mode ? (size_t)nwd * nper : nper;   // a bucket set holds <= n (table: nwd * n) entries
       if (AL) set_cap = (set_cap >> AL) + B + 1;                 // ... of which ceil(run / 2^AL) per bucket survive the affine levels
-      max_slices = ((size_t)nw * set_cap + KACC - 1) / KACC;
+      const size_t list_cap = (size_t)nw * set_cap;
+      max_slices = fit_threads ? accumulate_waves(list_cap, fit_threads, KACC) * fit_threads : (list_cap + KACC - 1) / KACC;
     }
     const size_t max_fix = (max_slices + KFIX - 1) / KFIX;
     E.part_pts[0].ensure(max_slices * XYZZ_BYTES); E.part_keys[0].ensure(max_slices * 4);
@@ -652,7 +659,7 @@ host::HXyzz<typename C::H> msm_device(Engine& E, const void* d_scalars, const vo
       dim3 block(B200_ACC_THREADS), grid((unsigned)((max_slices + B200_ACC_THREADS - 1) / B200_ACC_THREADS));
       k_accumulate<T><<<grid, block, 0, s>>>(keys, vals, (const unsigned long long*)E.bounds.ptr, 0, nw, no_key, (const uint32_t*)acc_points,
                                              (uint32_t*)E.buckets.ptr, (uint32_t*)E.part_pts[0].ptr, (uint32_t*)E.part_keys[0].ptr, max_slices, KACC,
-                                             into ? 1 : 0);
+                                             into ? 1 : 0, fit_threads);
       launches++;
     }
     if (timed) B200_CUDA_CHECK(cudaEventRecord(E.ev[3], s));

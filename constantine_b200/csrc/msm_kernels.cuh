@@ -121,13 +121,35 @@ constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 #ifndef B200_ACC_THREADS
 #define B200_ACC_THREADS 128
 #endif
+// Slice length that makes ceil(n / K) slices fill m = ceil(n / (fit_threads * k_max)) resident waves exactly: K = ceil(n / (m * fit_threads)),
+// at least B200_ACC_MIN_SLICE (tiny inputs: one partial wave). Then ceil(n / K) <= m * fit_threads for every n, and m is monotone
+// in n, so a grid of m(n_upper_bound) * fit_threads threads covers any actual n <= n_upper_bound.
+#ifndef B200_ACC_MIN_SLICE
+#define B200_ACC_MIN_SLICE 16
+#endif
+__host__ __device__ inline size_t accumulate_waves(size_t n, uint32_t fit_threads, int k_max) {
+  const size_t per_wave = (size_t)fit_threads * (size_t)k_max;
+  const size_t m = (n + per_wave - 1) / per_wave;
+  return m < 1 ? 1 : m;
+}
+__host__ __device__ inline int accumulate_slice_len(size_t n, uint32_t fit_threads, int k_max) {
+  const size_t per = accumulate_waves(n, fit_threads, k_max) * (size_t)fit_threads;
+  const size_t k = (n + per - 1) / per;
+  return k < B200_ACC_MIN_SLICE ? B200_ACC_MIN_SLICE : (int)k;
+}
+
 template <class T>
 __global__ void __launch_bounds__(B200_ACC_THREADS, (T::WORDS <= 12) ? B200_ACC_MIN_BLOCKS : 1)
 k_accumulate(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, const unsigned long long* __restrict__ bounds,
              int w0, int w1, uint32_t no_key, const uint32_t* __restrict__ points, uint32_t* buckets, uint32_t* part_pts,
-             uint32_t* part_keys, size_t max_slices, int K, int into) {
+             uint32_t* part_keys, size_t max_slices, int K, int into, uint32_t fit_threads) {
   // entries of windows [w0, w1) occupy sorted positions [begin, total); slices are counted from `begin`
   const size_t begin = (size_t)bounds[w0], total = (size_t)bounds[w1];
+  // `fit_threads` != 0 (the number of threads of this kernel the device keeps resident): K is the upper limit and the slice length is
+  // chosen HERE, from the actual entry count, so that the slices fill a whole number m of resident waves -- every thread of a wave
+  // walks the same number of entries, so a last wave that is 10% full costs as much as a full one (accumulate_slice_len, the host
+  // twin that sizes the grid, has the arithmetic)
+  if (fit_threads) K = accumulate_slice_len(total - begin, fit_threads, K);
   const size_t num_slices = (total - begin + (size_t)K - 1) / (size_t)K;
   __shared__ uint32_t head_smem[B200_ACC_THREADS * 4 * T::WORDS];
   const unsigned lane = threadIdx.x & 31u;

@@ -18,7 +18,7 @@ def main():
     ap.add_argument("--levels", default="0,1,2,3,4")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--cs", default="0", help="forced window sizes to sweep (0 = the engine's choice)")
-    ap.add_argument("--slice", type=int, default=0, help="forced slice length K of k_accumulate (0 = automatic)")
+    ap.add_argument("--slice", type=int, default=0, help="forced slice length K of k_accumulate (0 = automatic, -k = automatic with upper limit k)")
     ap.add_argument("--win", default="", help="begin:end -- only this window range (the shard of one rank of a window-sharded multi-GPU run; no result check)")
     a = ap.parse_args()
     import torch
@@ -39,7 +39,7 @@ def main():
     want = pyref.ec_mul_fast(e, cv.gen, cv)
     d_pts = torch.from_numpy(pts).cuda()
     d_s = torch.from_numpy(s).cuda()
-    lib.ctt_b200_set_tuning(0, 0, a.slice if a.slice > 0 else -1)
+    lib.ctt_b200_set_tuning(0, 0, a.slice if a.slice != 0 else -1)
     for lv, fc in [(int(x), int(y)) for y in a.cs.split(",") for x in a.levels.split(",")]:
         lib.ctt_b200_set_affine_levels(lv)
         ok = True
