@@ -428,8 +428,26 @@ B200_DEV void group_butterfly(Xyzz<T>& acc, int lanes) {
   }
 }
 
+// Groups wider than a warp (64 or 128 lanes of a 128-thread block; groups are aligned, so warp `wid` belongs to the group that starts
+// at warp wid - wid % wg): after the in-warp butterfly every warp parks its sum in shared memory and the first warp of the group adds
+// the wg sums with a wg-lane butterfly -- log2(wg) more dependent additions instead of a longer serial part. Every thread of the
+// block must call it (one __syncthreads). The total ends up in lane 0 of the group's first warp.
+template <class T, bool INL>
+B200_DEV void block_group_finish(Xyzz<T>& acc, int lanes, uint32_t* smem) {
+  const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  const unsigned wg = (unsigned)lanes >> 5;
+  if (lane == 0) store_xyzz(smem, wid, acc);
+  __syncthreads();
+  if (wid % wg == 0) {
+    Xyzz<T> v = Xyzz<T>::inf();
+    if (lane < wg) v = load_xyzz<T>(smem, wid + lane);
+    group_butterfly<T, INL>(v, (int)wg);
+    acc = v;
+  }
+}
+
 // Blocks [0, row_blocks): out_rows[w*R + h] = sum_l bucket[w][h*C + l];  the others: out_cols[w*C + l] = sum_h bucket[w][h*C + l].
-// `lanes` (power of two <= 32) lanes share one sum; a block is a whole number of warps and every lane reaches the shuffles.
+// `lanes` (power of two <= 128) lanes share one sum; a block is a whole number of groups and every lane reaches the shuffles.
 template <class T, bool INL>
 __global__ void __launch_bounds__(128) k_rowcol_sums(const uint32_t* buckets, uint32_t buckets_per_window, int a, uint32_t num_windows,
                                                      int lanes_r, int lanes_c, unsigned row_blocks, uint32_t* out_rows, uint32_t* out_cols) {
@@ -455,7 +473,9 @@ __global__ void __launch_bounds__(128) k_rowcol_sums(const uint32_t* buckets, ui
       padd<T, INL>(acc, b);
     }
   }
-  group_butterfly<T, INL>(acc, lanes);
+  __shared__ uint32_t warp_sums[4 * 4 * T::WORDS];
+  group_butterfly<T, INL>(acc, lanes < 32 ? lanes : 32);
+  if (lanes > 32) block_group_finish<T, INL>(acc, lanes, warp_sums);   // uniform per block
   if (live && t == 0) store_xyzz(cols ? out_cols : out_rows, sum_id, acc);
 }
 
@@ -465,55 +485,62 @@ __global__ void __launch_bounds__(128) k_rowcol_sums(const uint32_t* buckets, ui
 // Then S_w = sum_q 2^q P_q.  out[w * (c - 1) + q].
 template <class T, bool INL>
 __global__ void __launch_bounds__(128) k_plane_sums(const uint32_t* row_sums, const uint32_t* col_sums, int a, int rbits,
-                                                    uint32_t num_windows, uint32_t* out) {
-  const unsigned lane = threadIdx.x & 31u;
-  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                                                    uint32_t num_windows, int lanes, uint32_t* out) {
+  // `lanes` = 32 (one warp per sum) or 128 (one block per sum: 4 more dependent additions saved on sums of 256 terms)
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t sum_id = g / (unsigned)lanes;
+  const uint32_t t = (uint32_t)(g % (unsigned)lanes);
   const uint32_t planes = (uint32_t)(rbits + a);
-  const bool live = warp < (size_t)planes * num_windows;
+  const bool live = sum_id < (size_t)planes * num_windows;
   Xyzz<T> acc = Xyzz<T>::inf();
   if (live) {
-    const uint32_t w = (uint32_t)(warp / planes), q = (uint32_t)(warp % planes);
+    const uint32_t w = (uint32_t)(sum_id / planes), q = (uint32_t)(sum_id % planes);
     const bool is_h = q >= (uint32_t)a;
     const uint32_t bit = is_h ? q - (uint32_t)a : q;
     const uint32_t len = is_h ? (1u << rbits) : (1u << a);
     const uint32_t* src = is_h ? row_sums : col_sums;
     const size_t base = (size_t)w * len;
 #pragma unroll 1
-    for (uint32_t i = lane; i < len; i += 32u) {
+    for (uint32_t i = t; i < len; i += (uint32_t)lanes) {
       const uint32_t weight = is_h ? i : i + 1u;
       if ((weight >> bit) & 1u) {
         Xyzz<T> b = load_xyzz<T>(src, base + i);
         padd<T, INL>(acc, b);
       }
     }
-    if (q == (uint32_t)a && lane == 0) {
+    if (q == (uint32_t)a && t == 0) {
       Xyzz<T> b = load_xyzz<T>(col_sums, (size_t)w * (1u << a) + ((1u << a) - 1u));
       padd<T, INL>(acc, b);
     }
   }
+  __shared__ uint32_t warp_sums[4 * 4 * T::WORDS];
   group_butterfly<T, INL>(acc, 32);
-  if (live && lane == 0) store_xyzz(out, warp, acc);
+  if (lanes > 32) block_group_finish<T, INL>(acc, lanes, warp_sums);
+  if (live && t == 0) store_xyzz(out, sum_id, acc);
 }
 
-// Radix-16 digits of the window sums: out[w * groups + g] = sum_{k<4} 2^k P_{4g+k} (three doublings and up to three additions per
-// thread), so that the host tail adds one point per FOUR bit positions instead of one per position.
+// Radix-16 digits of the window sums: out[w * groups + g] = sum_{k<4} 2^k P_{4g+k}, so that the host tail adds one point per FOUR
+// bit positions instead of one per position. Four lanes per digit: lane k doubles P_{4g+k} k times, a 4-lane butterfly adds them
+// (at most 3 + 2 dependent operations; a single thread per digit needs 8).
 template <class T, bool INL>
 __global__ void __launch_bounds__(64) k_plane_combine(const uint32_t* planes_in, uint32_t planes, uint32_t groups, uint32_t num_windows,
                                                       uint32_t* out) {
-  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= (size_t)groups * num_windows) return;
-  const uint32_t w = (uint32_t)(g / groups), grp = (uint32_t)(g % groups);
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t g = t >> 2;
+  const uint32_t k = (uint32_t)(t & 3u);
+  const bool live = g < (size_t)groups * num_windows;
   Xyzz<T> r = Xyzz<T>::inf();
-#pragma unroll 1
-  for (int k = 3; k >= 0; k--) {
-    pdbl<T, INL>(r);
-    const uint32_t q = 4u * grp + (uint32_t)k;
+  if (live) {
+    const uint32_t w = (uint32_t)(g / groups), grp = (uint32_t)(g % groups);
+    const uint32_t q = 4u * grp + k;
     if (q < planes) {
-      Xyzz<T> b = load_xyzz<T>(planes_in, (size_t)w * planes + q);
-      padd<T, INL>(r, b);
+      r = load_xyzz<T>(planes_in, (size_t)w * planes + q);
+#pragma unroll 1
+      for (uint32_t i = 0; i < k; i++) pdbl<T, INL>(r);
     }
   }
-  store_xyzz(out, g, r);
+  group_butterfly<T, INL>(r, 4);
+  if (live && k == 0) store_xyzz(out, g, r);
 }
 
 // Batch tail: one thread per MSM of a batch. parts[(m * nwd + w) * row + i] are the <= 4 partial sums of window w of
