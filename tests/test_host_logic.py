@@ -182,3 +182,41 @@ def test_point_piece_boundaries_match_the_pair_classification():
             for i in {0, n - 1, n // 2, *(min(n - 1, x) for x in lo[:-1]), *(max(0, x - 1) for x in lo[1:]), rnd.randrange(n)}:
                 q = min(P - 1, i * P // n)
                 assert lo[q] <= i < lo[q + 1], (n, P, i, q)
+
+
+def test_accumulate_slice_fit_covers_every_entry_count():
+    """msm_kernels.cuh accumulate_waves / accumulate_slice_len: the kernel picks the slice length K from the ACTUAL entry count n, the host
+    sizes the grid from its upper bound of n. Restated here to pin the two properties the launch relies on: (1) ceil(n / K) slices never
+    exceed m(n) * threads, (2) m is monotone in n -- so a grid of m(n_upper) * threads covers any n <= n_upper; and K stays within
+    [16, limit] once a wave is full."""
+    MIN_SLICE = 16
+
+    def waves(n, threads, k_max):
+        per_wave = threads * k_max
+        return max(1, -(-n // per_wave))
+
+    def slice_len(n, threads, k_max):
+        per = waves(n, threads, k_max) * threads
+        return max(MIN_SLICE, -(-n // per))
+
+    import random
+    r = random.Random(20)
+    for threads in (148 * 2 * 128, 148 * 3 * 128, 148 * 128, 4 * 128):
+        for k_max in (32, 64, 128):
+            ns = [0, 1, 15, 16, 17, threads * MIN_SLICE - 1, threads * MIN_SLICE, threads * MIN_SLICE + 1,
+                  threads * k_max - 1, threads * k_max, threads * k_max + 1, 3 * threads * k_max + 7, 1 << 24, (1 << 31) - 1]
+            ns += [r.randrange(1, 1 << 27) for _ in range(300)]
+            prev_m = 0
+            for n in sorted(ns):
+                m, K = waves(n, threads, k_max), slice_len(n, threads, k_max)
+                assert m >= prev_m
+                prev_m = m
+                assert -(-n // K) <= m * threads                       # the grid of m waves holds every slice
+                assert MIN_SLICE <= K <= max(MIN_SLICE, k_max)
+                if n >= threads * MIN_SLICE:                           # a full wave: no slot of the m waves idles more than one entry's worth
+                    assert m * threads * (K - 1) < n + m * threads
+    # the shapes of profiles/slice_fit_r2t.txt (BLS12-381 G1: 2 blocks of 128 threads on 148 SMs)
+    t = 148 * 2 * 128
+    assert slice_len(2 * (1 << 20), t, 64) == 56            # 2 of 16 windows of N = 2^20: one wave
+    assert slice_len(20 * (1 << 16), t, 64) == 35           # N = 2^16, c = 13
+    assert slice_len(19 * (1 << 18), t, 64) == 44 and waves(19 * (1 << 18), t, 64) == 3
