@@ -8,7 +8,7 @@ Sources (dev container only):
   reference tests/protocol_ethereum_eip4844_deneb_kzg/blob_to_kzg_commitment/kzg-mainnet/*valid*/data.yaml
       (blob = 4096 x 32-byte big-endian Fr elements, output = 48-byte compressed commitment)
 commitment = sum_i blob[i] * srs_lagrange_brp[i]   (reference constantine/commitments/kzg.nim:186, parallel: kzg_parallel.nim:42)
-Output: tests/golden/kzg_commit_kat.npz  (SRS kept compressed: 4096 x 48 B; three blobs; their expected commitments).
+Output: tests/golden/kzg_commit_kat.npz  (SRS kept compressed: 4096 x 48 B; all seven valid blobs, densest first; their expected commitments).
 """
 import glob
 import os
@@ -54,8 +54,8 @@ def main():
         assert got == out, d
         print(os.path.basename(d), "non-zero scalars:", nz, "ok")
         blobs.append(np.frombuffer(blob, dtype=np.uint8)); outs.append(np.frombuffer(out, dtype=np.uint8)); names.append(os.path.basename(d))
-    # keep the three densest blobs (the fixture stays < 1 MB) plus record how many the exact tier verified
-    order = sorted(range(len(blobs)), key=lambda i: -int(np.count_nonzero(blobs[i])))[:3]
+    # all of them, densest first (the sparse ones compress to almost nothing); record how many the exact tier verified
+    order = sorted(range(len(blobs)), key=lambda i: -int(np.count_nonzero(blobs[i])))
     np.savez_compressed(os.path.join(HERE, "kzg_commit_kat.npz"),
                         srs_lagrange_brp_compressed=np.frombuffer(b"".join(srs_brp), dtype=np.uint8).reshape(4096, 48),
                         blobs=np.stack([blobs[i] for i in order]), commitments=np.stack([outs[i] for i in order]),
