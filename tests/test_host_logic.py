@@ -220,3 +220,50 @@ def test_accumulate_slice_fit_covers_every_entry_count():
     assert slice_len(2 * (1 << 20), t, 64) == 56            # 2 of 16 windows of N = 2^20: one wave
     assert slice_len(20 * (1 << 16), t, 64) == 35           # N = 2^16, c = 13
     assert slice_len(19 * (1 << 18), t, 64) == 44 and waves(19 * (1 << 18), t, 64) == 3
+
+
+@pytest.mark.parametrize("curve", list(CURVES))
+def test_combine_window_digits_is_the_weighted_sum(curve):
+    """ctt_b200_combine_window_digits = the host tail of every single MSM (msm_engine.cuh horner_window_digits: one doubling per bit
+    position, one addition per radix-16 digit point, on host_field.hpp): sum_w 2^(c w) sum_g 16^g D_{w,g} against the exact tier, for
+    every coordinate field (6- and 4-limb Fp, both Fp2), with empty digits and repeated points in the list."""
+    from constantine_b200 import msm as M
+    cv = CURVES[curve]
+    ks, pool = point_pool(cv)
+    c = 9
+    W = 255 // c + 1
+    groups = M.digits_per_window(c)
+    assert groups == 2
+    parts, scalar = [], 0
+    for w in range(W):
+        for g in range(groups):
+            i = (5 * w + 3 * g) % len(pool)
+            if (w + g) % 7 == 3:
+                parts.append(affine_to_xyzz_bytes(None, cv))
+                continue
+            parts.append(affine_to_xyzz_bytes(pool[i], cv))
+            scalar += ks[i] << (c * w + 4 * g)
+    want = pyref.ec_mul_fast(scalar % cv.fr.modulus, cv.gen, cv)
+    raw = b"".join(parts)
+    assert pyref.jac_bytes_to_affine(M.combine_window_digits(cv, raw, c, W, out=M.OUT_JAC), cv) == want
+    assert pyref.prj_bytes_to_affine(M.combine_window_digits(cv, raw, c, W, out=M.OUT_PRJ), cv) == want
+    assert xyzz_bytes_to_affine(M.combine_window_digits(cv, raw, c, W, out=M.OUT_XYZZ), cv) == want
+
+
+def test_host_multiplication_mulx_adx_matches_portable(tmp_path):
+    """host_field.hpp picks a MULX / ADCX / ADOX multiplication at run time on x86-64 hosts that have BMI2 + ADX. tools/bench_host_field.cpp
+    compares it with the portable CIOS form on ~10^6 operand pairs per field (edge values: 0, 1, p-1, p-2, all-ones limbs; random;
+    long chains of dependent products) -- built and run here with the host compiler."""
+    import shutil
+    import subprocess
+    from helpers import ROOT
+    import os
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "bench_host_field")
+    subprocess.check_call([cxx, "-O2", "-D__host__=", "-D__device__=", "-I", os.path.join(ROOT, "constantine_b200", "csrc"),
+                           os.path.join(ROOT, "tools", "bench_host_field.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count(" ok") == 4 and "MISMATCH" not in out.stdout
